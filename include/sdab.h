@@ -1,0 +1,187 @@
+/*
+ * sdab.h -- C ABI of libsdab, the sm_100a CUDA library behind sda_b200.
+ *
+ * This is the drop-in boundary for the SDA hot path.  The
+ * reference (francois-rozet/sda) has no FFI layer: its operator API is the Python
+ * classes in sda/nn.py, sda/score.py and sda/mcs.py.  Each entry point below
+ * therefore cites the reference method whose arithmetic it replaces; the Python
+ * classes in sda_b200/ keep the reference signatures and call these through
+ * ctypes (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are dense, row-major, float32, in the reference's own layouts
+ *     (NCHW for images, (B, L, C, H, W) for trajectories);
+ *   - all work is enqueued asynchronously on `stream` (a cudaStream_t passed as
+ *     void*); no hidden synchronisation, no internal allocation of tensors:
+ *     the caller (PyTorch) owns every buffer, including workspaces;
+ *   - functions return 0 on success and a non-zero code otherwise;
+ *     sdab_last_error() returns a message for the calling thread;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device the
+ *     compute entry points fail with SDAB_ERR_DEVICE.
+ */
+#ifndef SDAB_H_
+#define SDAB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDAB_OK 0
+#define SDAB_ERR_ARG 1      /* unsupported shape / argument                  */
+#define SDAB_ERR_DEVICE 2   /* no sm_100 device, or CUDA runtime failure     */
+#define SDAB_ERR_STATE 3    /* call order (weights not set, no saved state)  */
+
+#define SDAB_MAX_DEPTH 8
+
+/* arithmetic mode of the tensor-core convolutions */
+#define SDAB_MODE_BF16X3 0  /* 2-term bf16 split, 3 MMAs / product: fp32-grade parity (default) */
+#define SDAB_MODE_BF16 1    /* single bf16 pass: fast mode, ~5e-3 rel. error                   */
+
+/* convolution engine (debug / validation) */
+#define SDAB_ENGINE_UMMA 0  /* tcgen05 implicit GEMM (product path)        */
+#define SDAB_ENGINE_SIMT 1  /* fp32 CUDA-core implicit GEMM (cross-check)  */
+
+#define SDAB_ACT_SILU 0
+#define SDAB_ACT_RELU 1
+
+const char* sdab_last_error(void);
+int sdab_version(void);
+/* 0 when an sm_100 device is current and usable */
+int sdab_device_check(void);
+
+/* ------------------------------------------------------------------------- *
+ * U-Net  (reference: sda/nn.py:94-206 UNet, :18-28 ModResidualBlock)
+ * ------------------------------------------------------------------------- */
+
+typedef struct sdab_unet sdab_unet;
+
+typedef struct sdab_unet_desc {
+  int in_channels;                       /* UNet(in_channels, ...)            nn.py:96  */
+  int out_channels;                      /*                                   nn.py:97  */
+  int mod_features;                      /*                                   nn.py:98  */
+  int depth;                             /* len(hidden_channels)                         */
+  int hidden_channels[SDAB_MAX_DEPTH];   /*                                   nn.py:99  */
+  int hidden_blocks[SDAB_MAX_DEPTH];     /*                                   nn.py:100 */
+  int activation;                        /* SDAB_ACT_*                        nn.py:103 */
+} sdab_unet_desc;
+
+/* kernel_size 3, stride 2, spatial 2, padding_mode 'circular' only (the
+ * Kolmogorov configuration, experiments/kolmogorov/utils.py:59-68). */
+int sdab_unet_create(const sdab_unet_desc* desc, sdab_unet** out);
+void sdab_unet_destroy(sdab_unet* h);
+
+/* Number of convolutions / modulated blocks, in forward execution order:
+ * convs : head0, descent[0][*].{conv1,conv2}, head1, ..., ascent (deepest first)
+ *         blocks, each followed by its tail conv.
+ * blocks: descent[0][*], descent[1][*], ..., ascent[0][*] (deepest), ...        */
+int sdab_unet_num_convs(const sdab_unet* h);
+int sdab_unet_num_blocks(const sdab_unet* h);
+/* (C_out, C_in) of convolution i */
+int sdab_unet_conv_shape(const sdab_unet* h, int i, int* c_out, int* c_in);
+
+/* Bytes of the packed-weight buffer the caller must provide. */
+size_t sdab_unet_packed_bytes(const sdab_unet* h);
+
+/* Packs all parameters into `packed` (bf16 hi/lo, K-major per tap, forward and
+ * transposed/flipped for the input-gradient).  conv_w[i]: (C_out, C_in, 3, 3),
+ * conv_b[i]: (C_out); proj_w[j]: (C_j, mod), proj_b[j]: (C_j): nn.py:132-135.
+ * The arrays of pointers live on the HOST; the pointed tensors on the device. */
+int sdab_unet_set_weights(sdab_unet* h, const float* const* conv_w_host, const float* const* conv_b_host,
+                          const float* const* proj_w_host, const float* const* proj_b_host, void* packed,
+                          size_t packed_bytes, void* stream);
+
+/* Workspace needed for N images of H x W.  save != 0 keeps what dgrad needs. */
+size_t sdab_unet_workspace_bytes(const sdab_unet* h, int N, int H, int W, int save);
+
+/* UNet.forward(x, y)  nn.py:184-206.
+ * x: (N, in_channels, H, W); y: (Nt, mod_features), Nt in {1, N}; out: (N, out_channels, H, W). */
+int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
+                      void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream);
+
+/* Vector-Jacobian product w.r.t. x of the last forward run with save != 0 on the
+ * same workspace: gx = J_x^T gout (what torch.autograd.grad does through the
+ * reference UNet in GaussianScore.forward, score.py:381-394). */
+int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
+                    int engine, void* stream);
+
+/* One 3x3 circular convolution on NCHW fp32 tensors (nn.Conv2d(kernel_size=3, padding=1,
+ * padding_mode='circular', stride), sda/nn.py:125-128,151-157).  weight: (Cout, Cin, 3, 3); bias:
+ * (Cout) or NULL; out: (N, Cout, H/stride, W/stride).  transpose != 0 (stride 1) computes the
+ * input-gradient instead: x: (N, Cout, H, W) -> out: (N, Cin, H, W), bias must be NULL. */
+size_t sdab_conv3x3_workspace_bytes(int N, int Cin, int Cout, int H, int W, int stride, int transpose);
+int sdab_conv3x3(const float* x, const float* weight, const float* bias, float* out, int N, int Cin, int Cout, int H,
+                 int W, int stride, int transpose, int mode, int engine, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Number of kernels launched by this library on the calling thread since the last reset. */
+long long sdab_launch_count(int reset);
+
+/* ------------------------------------------------------------------------- *
+ * Window maps  (reference: sda/score.py:146-164 MCScoreNet.unfold / fold)
+ * ------------------------------------------------------------------------- */
+
+/* unfold + channel concat of a broadcast context (ScoreUNet.forward's torch.cat, score.py:87):
+ * x: (B, L, C, H, W) -> win: (B, L-2k, (2k+1) C + Cc, H, W); ctx: (Cc, H, W) or NULL. */
+int sdab_unfold_cat(const float* x, const float* ctx, float* win, int B, int L, int C, int Cc, int H, int W, int order,
+                    void* stream);
+/* fold: win_out: (B, L-2k, (2k+1) C, H, W) -> s: (B, L, C, H, W)  score.py:155-164 */
+int sdab_fold(const float* win_out, float* s, int B, int L, int C, int H, int W, int order, void* stream);
+/* adjoint of fold: scatter of the cotangent into zero-initialised windows */
+int sdab_fold_transpose(const float* gs, float* gwin, int B, int L, int C, int H, int W, int order, void* stream);
+/* adjoint of unfold_cat w.r.t. x: deterministic overlap-add (autograd UnfoldBackward0) */
+int sdab_unfold_transpose_add(const float* gwin, float* gx, int B, int L, int C, int Cc, int H, int W, int order,
+                              void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * Sampler updates  (reference: sda/score.py:250-261 VPSDE.sample loop body)
+ * ------------------------------------------------------------------------- */
+
+/* predictor: x <- a * x + b * eps */
+int sdab_vpsde_predict(float* x, const float* eps, float a, float b, size_t n, void* stream);
+/* corrector: per batch element i (event = n / B values):
+ *   delta_i = tau / mean(eps_i^2);  x <- x - (delta_i * eps + sqrt(2 delta_i) * z) * sigma
+ * z ~ N(0, 1) from a counter-based Philox keyed by (seed, global element index), or read from
+ * `z` when it is not NULL (noise injection for parity tests).
+ * scratch: sdab_vpsde_correct_scratch_floats(B) floats. */
+size_t sdab_vpsde_correct_scratch_floats(int B);
+int sdab_vpsde_correct(float* x, const float* eps, const float* z, float tau, float sigma, uint64_t seed,
+                       uint64_t offset, int B, size_t n, float* scratch, void* stream);
+/* standard normal draw with the same Philox stream (x(1) initialisation) */
+int sdab_randn(float* out, size_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* Tweedie estimate and final combination of GaussianScore.forward (score.py:387,396):
+ *   xhat = (x - sigma * eps) / mu ;   out = eps - sigma * s                                  */
+int sdab_tweedie(const float* x, const float* eps, float mu, float sigma, float* xhat, size_t n, void* stream);
+int sdab_axpy(const float* a, const float* b, float alpha, float* out, size_t n, void* stream); /* out = a + alpha b */
+
+/* ------------------------------------------------------------------------- *
+ * Kolmogorov flow  (reference: sda/mcs.py:244-338 KolmogorovFlow, i.e. jax-cfd's
+ * semi_implicit_navier_stokes finite-volume step + FFT pressure projection)
+ * ------------------------------------------------------------------------- */
+
+typedef struct sdab_kolmogorov sdab_kolmogorov;
+
+int sdab_kolmogorov_create(int size, double dt, double reynolds, sdab_kolmogorov** out);
+void sdab_kolmogorov_destroy(sdab_kolmogorov* h);
+int sdab_kolmogorov_inner_steps(const sdab_kolmogorov* h);
+size_t sdab_kolmogorov_workspace_bytes(const sdab_kolmogorov* h, int E);
+/* uv: (E, 2, size, size), advanced in place by n_transitions transitions (mcs.py:333-338);
+ * when traj != NULL every transition is also written to traj: (n_transitions, E, 2, size, size). */
+int sdab_kolmogorov_transition(sdab_kolmogorov* h, float* uv, int E, int n_transitions, float* traj, void* workspace,
+                               size_t workspace_bytes, void* stream);
+/* prior (mcs.py:321-331): filtered random velocity field, max speed 3, peak wavenumber 4 */
+int sdab_kolmogorov_prior(sdab_kolmogorov* h, float* uv, int E, uint64_t seed, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* observation helpers (mcs.py:340-347, :361-375) */
+int sdab_coarsen(const float* x, float* out, size_t n_img, int H, int W, int r, void* stream);
+int sdab_vorticity(const float* x, float* out, size_t n_pair, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SDAB_H_ */

@@ -1,0 +1,214 @@
+// common.cuh -- shared declarations of libsdab (sm_100a only).
+//
+// Internal activation formats (DESIGN.md "Data layout in HBM"):
+//   F(C)   fp32, NHWC           [N][H][W][C]
+//   OP(C)  bf16 hi/lo operand   [N][H+2][W+2][2][C]   -- plane 0 = hi, plane 1 = lo,
+//          physically haloed: the ring replicates the opposite edge (circular padding,
+//          nn.Conv2d(padding_mode='circular'), sda/nn.py:125-128) so that every 3x3 tap of
+//          every tile is one in-bounds TMA box.
+//   OP/S2  the same pixels de-interleaved by (row, column) parity:
+//          [N][4][(H+2)/2][(W+2)/2][2][C] -- the input format of the stride-2 heads
+//          (sda/nn.py:151-159), again so that each tap is one dense TMA box.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/sdab.h"
+
+namespace sdab {
+
+// ----------------------------------------------------------------------------- errors
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+void count_launch(int n = 1);
+
+#define SDAB_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::sdab::fail(SDAB_ERR_DEVICE, std::string(#expr) + ": " + cudaGetErrorString(_e));    \
+  } while (0)
+
+#define SDAB_LAUNCH_CHECK(name)                                                                    \
+  do {                                                                                             \
+    ::sdab::count_launch();                                                                        \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess)                                                                         \
+      return ::sdab::fail(SDAB_ERR_DEVICE, std::string("launch of ") + name + ": " +              \
+                                               cudaGetErrorString(_e));                            \
+  } while (0)
+
+#define SDAB_REQUIRE(cond, msg)                                                                    \
+  do {                                                                                             \
+    if (!(cond)) return ::sdab::fail(SDAB_ERR_ARG, std::string(msg) + " [" #cond "]");             \
+  } while (0)
+
+#define SDAB_TRY(expr)                                                                             \
+  do {                                                                                             \
+    int _s = (expr);                                                                               \
+    if (_s != SDAB_OK) return _s;                                                                  \
+  } while (0)
+
+typedef __nv_bfloat16 bf16;
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// ----------------------------------------------------------------------------- operand layout
+struct OpShape {
+  int N, H, W, C;  // logical image size, channels (multiple of 16)
+  int s2;          // 1: parity de-interleaved layout
+  __host__ __device__ size_t elems() const { return (size_t)N * (H + 2) * (W + 2) * 2 * C; }
+  __host__ __device__ size_t bytes() const { return elems() * 2; }
+};
+
+// element offset of the hi plane of padded pixel (hp, wp) of image n; the lo plane is +C
+__host__ __device__ __forceinline__ size_t op_offset(const OpShape& s, int n, int hp, int wp) {
+  const int Hp = s.H + 2, Wp = s.W + 2;
+  if (!s.s2) return (((size_t)n * Hp + hp) * Wp + wp) * 2 * s.C;
+  const int par = (hp & 1) * 2 + (wp & 1);
+  return ((((size_t)n * 4 + par) * (Hp >> 1) + (hp >> 1)) * (Wp >> 1) + (wp >> 1)) * 2 * s.C;
+}
+
+// Calls f(hp, wp) for the padded positions that hold logical pixel (h, w): itself plus its
+// halo replicas (up to 4).
+template <class F>
+__device__ __forceinline__ void for_each_replica(int h, int w, int H, int W, F&& f) {
+  const int hp = h + 1, wp = w + 1;
+  const int hr = (h == 0) ? H + 1 : ((h == H - 1) ? 0 : -1);
+  const int wr = (w == 0) ? W + 1 : ((w == W - 1) ? 0 : -1);
+  f(hp, wp);
+  if (hr >= 0) f(hr, wp);
+  if (wr >= 0) f(hp, wr);
+  if (hr >= 0 && wr >= 0) f(hr, wr);
+}
+
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  if (act == 1) return v / (1.f + __expf(-v));  // SiLU
+  if (act == 2) return fmaxf(v, 0.f);           // ReLU
+  return v;
+}
+
+// derivative of the activation at pre-activation c
+__device__ __forceinline__ float act_bwd(float c, int act) {
+  if (act == 1) {
+    const float s = 1.f / (1.f + __expf(-c));
+    return s * (1.f + c * (1.f - s));
+  }
+  if (act == 2) return c > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
+
+// ----------------------------------------------------------------------------- conv problem
+struct ConvEpilogue {
+  const float* bias;   // [Cout] or null
+  const float* res;    // F(Cout) residual added before anything else, or null
+  float* pre;          // F(Cout): v = acc + bias + res saved here (pre-activation), or null
+  const float* dact;   // F(Cout): result multiplied by act'(dact) (backward of the activation), or null
+  float* outF;         // F(Cout) or null
+  bf16* outOP;         // OP(Cout) (normal layout, halo written) or null
+  int act;             // forward activation applied to v: 0 none, 1 SiLU, 2 ReLU
+  int dact_kind;       // which activation's derivative `dact` refers to (1 SiLU, 2 ReLU)
+};
+
+struct ConvProblem {
+  const bf16* in;      // OP(Cin) at resolution (H*stride, W*stride); S2 layout iff stride == 2
+  const bf16* wpk;     // packed weights [9][Cin/32][2][Cout][32]
+  int N, H, W;         // OUTPUT resolution
+  int Cin, Cout;       // padded: Cin % 32 == 0, Cout % 16 == 0
+  int stride;          // 1 or 2
+  int mode;            // SDAB_MODE_*
+  ConvEpilogue epi;
+};
+
+int conv3x3_simt(const ConvProblem& p, cudaStream_t stream);
+int conv3x3_umma(const ConvProblem& p, cudaStream_t stream);
+
+// Applies the epilogue to 16 consecutive output channels [c0, c0+16) of one pixel.
+// pix = (n*H + h)*W + w.  Shared by both engines so that they agree bit for bit in everything
+// but the accumulation order.
+__device__ __forceinline__ void epilogue_store16(const ConvEpilogue& e, float (&v)[16], size_t pix, int n, int h,
+                                                 int w, int H, int W, int Cout, int c0) {
+  const size_t off = pix * Cout + c0;
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + j));
+      v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+    }
+  }
+  if (e.res) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 r = *reinterpret_cast<const float4*>(e.res + off + j);
+      v[j] += r.x, v[j + 1] += r.y, v[j + 2] += r.z, v[j + 3] += r.w;
+    }
+  }
+  if (e.pre) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(e.pre + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  if (e.act) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = act_fwd(v[j], e.act);
+  }
+  if (e.dact) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(e.dact + off + j);
+      v[j] *= act_bwd(c.x, e.dact_kind), v[j + 1] *= act_bwd(c.y, e.dact_kind);
+      v[j + 2] *= act_bwd(c.z, e.dact_kind), v[j + 3] *= act_bwd(c.w, e.dact_kind);
+    }
+  }
+  if (e.outF) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(e.outF + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+  }
+  if (e.outOP) {
+    __align__(16) bf16 hi[16];
+    __align__(16) bf16 lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
+    const OpShape s{0, H, W, Cout, 0};
+    for_each_replica(h, w, H, W, [&](int hp, int wp) {
+      bf16* dst = e.outOP + op_offset(s, n, hp, wp) + c0;
+      reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(hi)[0];
+      reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(hi)[1];
+      reinterpret_cast<uint4*>(dst + Cout)[0] = reinterpret_cast<const uint4*>(lo)[0];
+      reinterpret_cast<uint4*>(dst + Cout)[1] = reinterpret_cast<const uint4*>(lo)[1];
+    });
+  }
+}
+
+// ----------------------------------------------------------------------------- elementwise launches
+int pack_nchw_to_op(const float* x, bf16* op, int N, int Creal, int Cpad, int H, int W, int s2, cudaStream_t st);
+int unpack_f_to_nchw(const float* f, float* x, int N, int Creal, int Cpad, int H, int W, cudaStream_t st);
+// kind: 0 normal, 1 S2 (parity) layout, 2 zero-insertion x2 upsample (src at half resolution)
+int f_to_operand(const float* f, bf16* op, int N, int H, int W, int C, int kind, cudaStream_t st);
+// LN over channels of (x + shift) -> OP (optionally nearest x2 upsampled); rstd saved when not null.
+// shift: [Nt][shift_stride] slice starting at channel 0 of this block, or null.
+int ln_forward(const float* x, const float* shift, int shift_stride, int Nt, bf16* op, float* rstd, int N, int H, int W,
+               int C, int upsample, cudaStream_t st);
+// backward of LN: ga (optionally 2x2 sum-pooled from resolution 2H x 2W), a = hi+lo read from the
+// saved operand (at (2h,2w) of the upsampled operand when upsample), gx = res + gu.
+int ln_backward(const float* ga, const bf16* a_op, const float* rstd, const float* res, float* gxF, bf16* gxOP, int N,
+                int H, int W, int C, int pooled, cudaStream_t st);
+int time_shifts(const float* y, const float* pw, const float* pb, float* out, int Nt, int rows, int mod,
+                cudaStream_t st);
+int pack_conv_weights(const float* w, bf16* fwd, bf16* bwd, int Cout, int Cin, cudaStream_t st);
+int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
+int fill_zero(void* p, size_t bytes, cudaStream_t st);
+
+}  // namespace sdab

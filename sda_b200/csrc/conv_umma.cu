@@ -1,0 +1,383 @@
+// conv_umma.cu -- tcgen05 implicit-GEMM 3x3 circular convolution for sm_100a (product engine).
+//
+// Replaces nn.Conv2d(kernel_size=3, padding=1, padding_mode='circular', stride in {1,2}) as built
+// by sda/nn.py:125-174, forward and (with transposed/flipped packed weights) input-gradient.
+//
+//   GEMM view    D[m, co] = sum_{tap, ci} A_tap[m, ci] * W[tap][co, ci]
+//                M = 128 output pixels (one TileGeom box), N = C_out (<= 512 fp32 TMEM columns),
+//                K = 9 taps x C_in, walked in 32-channel blocks (64 B rows, SWIZZLE_64B).
+//   A operand    one TMA box per (tap, 32-channel block, hi|lo plane) of the haloed NHWC operand
+//                tensor: the circular wrap is already materialised in the halo ring, so every box
+//                is in bounds; stride-2 heads read the parity de-interleaved layout instead.
+//   B operand    one (two for C_out > 256) TMA box per (tap, block, plane) of the packed weights.
+//   precision    SDAB_MODE_BF16X3: x = hi + lo in bf16; hi*hi + hi*lo + lo*hi accumulated in the same
+//                fp32 TMEM accumulator (3 MMAs per product, ~2^-16 relative error);
+//                SDAB_MODE_BF16: hi*hi only.
+//   schedule     persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA
+//                issuer (one elected lane) + TMEM allocator, warps 2-5 = epilogue (TMEM -> registers ->
+//                fused bias / residual / activation / activation-derivative / bf16 split -> global).
+//                smem ring of `stages` K-blocks (full/empty mbarriers), TMEM accumulator double
+//                buffered when C_out <= 256 so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "tile_geom.h"
+
+namespace sdab {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = 128 * 64;  // one A box: 128 pixels x 32 channels x bf16
+constexpr uint32_t kCtrlBytes = 1024;
+constexpr uint32_t kSmemBudget = 227 * 1024;
+constexpr int kMaxStages = 8;
+
+struct UmmaParams {
+  TileGeom g;
+  int N, H, W, Cin, Cout, stride, nchunk;
+  int planes;      // 2 in bf16x3 mode (hi, lo), 1 in bf16 mode
+  int stages, acc_stages;
+  int CB, nb;      // N of one MMA, number of N halves
+  uint32_t b_plane_bytes, stage_bytes;
+  ConvEpilogue epi;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must abort the kernel (trap -> launch error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor: 8-row groups of 64 B rows, 512 B apart.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+// ------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+
+  const uint32_t bar_full = base;            // kMaxStages x 8 B
+  const uint32_t bar_empty = base + 64;      // kMaxStages x 8 B
+  const uint32_t bar_tfull = base + 128;     // 2 x 8 B
+  const uint32_t bar_tempty = base + 144;    // 2 x 8 B
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
+  const uint32_t stage0 = base + kCtrlBytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 160), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = 9 * p.nchunk;
+  const uint32_t acc_stride = p.acc_stages == 2 ? 256u : 0u;
+  const uint32_t b_off = p.planes * kABytes;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = p.planes * (kABytes + (uint32_t)p.Cout * 64u);
+      for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x) {
+        int n0, h0, w0;
+        p.g.tile_origin(tile, n0, h0, w0);
+        for (int tap = 0; tap < 9; ++tap) {
+          const int a = tap / 3, b = tap % 3;
+          int cw, ch, cp;
+          if (p.stride == 1) {
+            cw = w0 + b, ch = h0 + a, cp = 0;
+          } else {
+            cw = w0 + (b >> 1), ch = h0 + (a >> 1), cp = (a & 1) * 2 + (b & 1);
+          }
+          for (int chunk = 0; chunk < p.nchunk; ++chunk) {
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_expect_tx(full, tx_bytes);
+            const uint32_t sa = stage0 + stage * p.stage_bytes;
+            const int brow = ((tap * p.nchunk + chunk) * 2) * p.Cout;
+            for (int pl = 0; pl < p.planes; ++pl) {
+              tma_load_5d(sa + pl * kABytes, &tmA, full, chunk * 32 + pl * p.Cin, cw, ch, cp, n0);
+              for (int half = 0; half < p.nb; ++half)
+                tma_load_2d(sa + b_off + pl * p.b_plane_bytes + half * p.CB * 64, &tmB, full, 0,
+                            brow + pl * p.Cout + half * p.CB);
+            }
+            if (++stage == p.stages) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.CB >> 3) << 17) | ((128u >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it % p.acc_stages;
+        const uint32_t acc_phase = (it / p.acc_stages) & 1;
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * acc_stride;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = stage0 + stage * p.stage_bytes;
+          const uint32_t sb = sa + b_off;
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const int npass = p.planes == 2 ? 3 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
+              // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
+              const uint32_t aaddr = sa + (pass == 2 ? kABytes : 0) + kk * 32;
+              const uint32_t baddr = sb + (pass == 1 ? p.b_plane_bytes : 0) + kk * 32;
+              const uint64_t adesc = smem_desc_sw64(aaddr);
+              for (int half = 0; half < p.nb; ++half) {
+                const uint64_t bdesc = smem_desc_sw64(baddr + half * p.CB * 64);
+                umma_bf16(d0 + half * p.CB, adesc, bdesc, idesc, (kb | kk | pass) != 0);
+              }
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);
+          if (++stage == p.stages) stage = 0, phase ^= 1;
+        }
+        umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+    const int m = q * 32 + lane;
+    const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it % p.acc_stages;
+      const uint32_t acc_phase = (it / p.acc_stages) & 1;
+      int n0, h0, w0;
+      p.g.tile_origin(tile, n0, h0, w0);
+      const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+      const bool valid = n < p.N;
+      const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(t0 + c0, v);
+        if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.H, p.W, p.Cout, c0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box) {
+  auto fn = get_encode();
+  if (!fn) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return SDAB_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+}  // namespace
+
+int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
+  UmmaParams p{};
+  SDAB_TRY(make_tile_geom(c.N, c.H, c.W, p.g));
+  SDAB_REQUIRE(c.Cin % 32 == 0 && c.Cin >= 32, "C_in must be padded to a multiple of 32");
+  SDAB_REQUIRE(c.Cout % 16 == 0 && c.Cout >= 16 && c.Cout <= 512, "C_out must be a multiple of 16, at most 512");
+  SDAB_REQUIRE(c.stride == 1 || c.stride == 2, "stride must be 1 or 2");
+  p.N = c.N, p.H = c.H, p.W = c.W, p.Cin = c.Cin, p.Cout = c.Cout, p.stride = c.stride;
+  p.nchunk = c.Cin / 32;
+  p.planes = c.mode == SDAB_MODE_BF16X3 ? 2 : 1;
+  if (c.Cout <= 256) {
+    p.CB = c.Cout, p.nb = 1, p.acc_stages = 2;
+  } else {
+    SDAB_REQUIRE(c.Cout % 32 == 0, "C_out above 256 must be a multiple of 32");
+    p.CB = c.Cout / 2, p.nb = 2, p.acc_stages = 1;
+  }
+  p.b_plane_bytes = (uint32_t)round_up(c.Cout * 64, 1024);
+  p.stage_bytes = p.planes * (kABytes + p.b_plane_bytes);
+  p.stages = (int)((kSmemBudget - kCtrlBytes - 1024) / p.stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
+  p.epi = c.epi;
+
+  // A: haloed operand tensor at the input resolution
+  const int Hin = c.H * c.stride, Win = c.W * c.stride;
+  const cuuint64_t Hp = Hin + 2, Wp = Win + 2, C2 = 2 * (cuuint64_t)c.Cin;
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5], strides[4];
+    if (c.stride == 1) {
+      dims[0] = C2, dims[1] = Wp, dims[2] = Hp, dims[3] = 1, dims[4] = (cuuint64_t)c.N;
+      strides[0] = C2 * 2, strides[1] = Wp * C2 * 2, strides[2] = Hp * Wp * C2 * 2, strides[3] = Hp * Wp * C2 * 2;
+    } else {
+      dims[0] = C2, dims[1] = Wp / 2, dims[2] = Hp / 2, dims[3] = 4, dims[4] = (cuuint64_t)c.N;
+      strides[0] = C2 * 2, strides[1] = (Wp / 2) * C2 * 2, strides[2] = (Hp / 2) * (Wp / 2) * C2 * 2,
+      strides[3] = 4 * (Hp / 2) * (Wp / 2) * C2 * 2;
+    }
+    const cuuint32_t box[5] = {32, (cuuint32_t)p.g.BW, (cuuint32_t)p.g.BH, 1, (cuuint32_t)p.g.BN};
+    SDAB_TRY(encode(&tmA, c.in, 5, dims, strides, box));
+  }
+  {
+    const cuuint64_t dims[2] = {32, (cuuint64_t)9 * p.nchunk * 2 * c.Cout};
+    const cuuint64_t strides[1] = {64};
+    const cuuint32_t box[2] = {32, (cuuint32_t)p.CB};
+    SDAB_TRY(encode(&tmB, c.wpk, 2, dims, strides, box));
+  }
+
+  const size_t smem = kCtrlBytes + 1024 + (size_t)p.stages * p.stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
+  conv_umma_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  SDAB_LAUNCH_CHECK("conv_umma_kernel");
+  return SDAB_OK;
+}
+
+}  // namespace sdab

@@ -1,0 +1,359 @@
+// elementwise.cu -- HBM-bound kernels of the U-Net path: layout conversion, channel LayerNorm
+// forward/backward, time-shift projection and weight packing.
+//
+// All kernels map one warp to one pixel and lanes to channels (c = lane + 32 j), so every global
+// access of a warp is one contiguous 128 B (fp32) or 64 B (bf16) segment.
+#include "common.cuh"
+
+namespace sdab {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kChanTile = 64;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline dim3 warp_grid(size_t n_warps) { return dim3((unsigned)((n_warps + kWarpsPerBlock - 1) / kWarpsPerBlock)); }
+
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> OP(Cpad): the entry of the network.  ScoreUNet.forward hands the U-Net a
+// contiguous (N, C, H, W) tensor (sda/score.py:89-93).  Tile of 32 pixels along W through smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ op, int N, int Creal, int Cpad, int H,
+                                 int W, int s2) {
+  __shared__ float tile[kChanTile][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
+  const OpShape s{N, H, W, Cpad, s2};
+  for (int cb = 0; cb < Cpad; cb += kChanTile) {
+    const int nc = min(kChanTile, Cpad - cb);
+    __syncthreads();
+    for (int c = ty; c < nc; c += blockDim.y) {
+      float v = 0.f;
+      if (cb + c < Creal && w0 + tx < W) v = x[(((size_t)n * Creal + cb + c) * H + h) * W + w0 + tx];
+      tile[c][tx] = v;
+    }
+    __syncthreads();
+    for (int px = ty; px < 32; px += blockDim.y) {
+      const int w = w0 + px;
+      if (w >= W) continue;
+      for (int c = tx; c < nc; c += 32) {
+        bf16 hi, lo;
+        split_bf16(tile[c][px], hi, lo);
+        for_each_replica(h, w, H, W, [&](int hp, int wp) {
+          bf16* dst = op + op_offset(s, n, hp, wp);
+          dst[cb + c] = hi;
+          dst[Cpad + cb + c] = lo;
+        });
+      }
+    }
+  }
+}
+
+// F(Cpad) -> NCHW fp32 (first Creal channels): the exit of the network.
+__global__ void unpack_nchw_kernel(const float* __restrict__ f, float* __restrict__ x, int N, int Creal, int Cpad,
+                                   int H, int W) {
+  __shared__ float tile[kChanTile][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
+  for (int cb = 0; cb < Creal; cb += kChanTile) {
+    const int nc = min(kChanTile, Cpad - cb);
+    __syncthreads();
+    for (int px = ty; px < 32; px += blockDim.y) {
+      const int w = w0 + px;
+      if (w >= W) continue;
+      for (int c = tx; c < nc; c += 32) tile[c][px] = f[(((size_t)n * H + h) * W + w) * Cpad + cb + c];
+    }
+    __syncthreads();
+    for (int c = ty; c < nc && cb + c < Creal; c += blockDim.y)
+      if (w0 + tx < W) x[(((size_t)n * Creal + cb + c) * H + h) * W + w0 + tx] = tile[c][tx];
+  }
+}
+
+// F(C) -> OP(C).  kind 0: normal; 1: S2 parity layout; 2: zero-insertion x2 (f is at H/2 x W/2).
+__global__ void f_to_operand_kernel(const float* __restrict__ f, bf16* __restrict__ op, int N, int H, int W, int C,
+                                    int kind) {
+  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
+  const size_t total = (size_t)N * H * W;
+  if (warp >= total) return;
+  const int lane = threadIdx.x;
+  const int w = warp % W, h = (warp / W) % H, n = warp / ((size_t)W * H);
+  const OpShape s{N, H, W, C, kind == 1};
+  const float* src = nullptr;
+  if (kind == 2) {
+    if (!(h & 1) && !(w & 1)) src = f + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C;
+  } else {
+    src = f + warp * C;
+  }
+  for (int c = lane; c < C; c += 32) {
+    bf16 hi, lo;
+    split_bf16(src ? src[c] : 0.f, hi, lo);
+    for_each_replica(h, w, H, W, [&](int hp, int wp) {
+      bf16* dst = op + op_offset(s, n, hp, wp);
+      dst[c] = hi;
+      dst[C + c] = lo;
+    });
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Channel LayerNorm of (x + shift): zuko.nn.LayerNorm(dim=-3) as used at sda/nn.py:137,163 --
+// (u - mean_C u) / sqrt(var_C,unbiased(u) + 1e-5), no affine -- applied to u = x + project(y)
+// (ModResidualBlock.forward, sda/nn.py:27-28).  Output: bf16 hi/lo operand of the next conv,
+// optionally nearest-upsampled x2 (the tails, sda/nn.py:161-170).
+// ---------------------------------------------------------------------------------------------
+template <int MAXJ>
+__global__ void ln_forward_kernel(const float* __restrict__ x, const float* __restrict__ shift, int shift_stride,
+                                  int Nt, bf16* __restrict__ op, float* __restrict__ rstd, int N, int H, int W, int C,
+                                  int upsample) {
+  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
+  const size_t total = (size_t)N * H * W;
+  if (warp >= total) return;
+  const int lane = threadIdx.x;
+  const int w = warp % W, h = (warp / W) % H, n = warp / ((size_t)W * H);
+  const float* src = x + warp * C;
+  const float* sh = shift ? shift + (size_t)(Nt > 1 ? n : 0) * shift_stride : nullptr;
+  const int nj = C / 32;
+  float u[MAXJ];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    if (j < nj) {
+      const int c = lane + 32 * j;
+      u[j] = src[c] + (sh ? __ldg(sh + c) : 0.f);
+      sum += u[j];
+    }
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    if (j < nj) {
+      u[j] -= mean;
+      sq += u[j] * u[j];
+    }
+  }
+  const float var = warp_sum(sq) / (C - 1);
+  const float r = 1.f / sqrtf(var + 1e-5f);
+  if (rstd && lane == 0) rstd[warp] = r;
+  const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
+  const OpShape s{N, Ho, Wo, C, 0};
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    if (j < nj) {
+      const int c = lane + 32 * j;
+      bf16 hi, lo;
+      split_bf16(u[j] * r, hi, lo);
+      const int reps = upsample ? 2 : 1;
+      for (int dh = 0; dh < reps; ++dh)
+        for (int dw = 0; dw < reps; ++dw) {
+          const int ho = upsample ? 2 * h + dh : h, wo = upsample ? 2 * w + dw : w;
+          for_each_replica(ho, wo, Ho, Wo, [&](int hp, int wp) {
+            bf16* dst = op + op_offset(s, n, hp, wp);
+            dst[c] = hi;
+            dst[C + c] = lo;
+          });
+        }
+    }
+  }
+}
+
+// Backward of the channel LayerNorm:
+//   gu = (ga - mean_C(ga) - a * sum_C(ga * a) / (C - 1)) * rstd ;  gx = res + gu
+// a is re-read from the saved operand (hi + lo).  pooled: ga is given at 2H x 2W and summed over
+// the 2x2 block first (adjoint of the nearest upsample of the tails), and the operand holding a is
+// the upsampled one (read at (2h, 2w)).
+template <int MAXJ>
+__global__ void ln_backward_kernel(const float* __restrict__ ga, const bf16* __restrict__ a_op,
+                                   const float* __restrict__ rstd, const float* __restrict__ res,
+                                   float* __restrict__ gxF, bf16* __restrict__ gxOP, int N, int H, int W, int C,
+                                   int pooled) {
+  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
+  const size_t total = (size_t)N * H * W;
+  if (warp >= total) return;
+  const int lane = threadIdx.x;
+  const int w = warp % W, h = (warp / W) % H, n = warp / ((size_t)W * H);
+  const int nj = C / 32;
+  const OpShape sa{N, pooled ? 2 * H : H, pooled ? 2 * W : W, C, 0};
+  const bf16* ap = a_op + op_offset(sa, n, (pooled ? 2 * h : h) + 1, (pooled ? 2 * w : w) + 1);
+  float g[MAXJ], a[MAXJ];
+  float sg = 0.f, sga = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    if (j < nj) {
+      const int c = lane + 32 * j;
+      if (pooled) {
+        const size_t W2 = 2 * (size_t)W;
+        const float* p = ga + (((size_t)n * 2 * H + 2 * h) * W2 + 2 * w) * C + c;
+        g[j] = (p[0] + p[C]) + (p[W2 * C] + p[W2 * C + C]);
+      } else {
+        g[j] = ga[warp * C + c];
+      }
+      a[j] = __bfloat162float(ap[c]) + __bfloat162float(ap[C + c]);
+      sg += g[j];
+      sga += g[j] * a[j];
+    }
+  }
+  sg = warp_sum(sg) / C;
+  sga = warp_sum(sga) / (C - 1);
+  const float r = rstd[warp];
+  const OpShape so{N, H, W, C, 0};
+#pragma unroll
+  for (int j = 0; j < MAXJ; ++j) {
+    if (j < nj) {
+      const int c = lane + 32 * j;
+      float v = (g[j] - sg - a[j] * sga) * r;
+      if (res) v += res[warp * C + c];
+      if (gxF) gxF[warp * C + c] = v;
+      if (gxOP) {
+        bf16 hi, lo;
+        split_bf16(v, hi, lo);
+        for_each_replica(h, w, H, W, [&](int hp, int wp) {
+          bf16* dst = gxOP + op_offset(so, n, hp, wp);
+          dst[c] = hi;
+          dst[C + c] = lo;
+        });
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// All `project` Linears of the network in one launch (sda/nn.py:132-135): out[nt][r] =
+// pb[r] + sum_m pw[r][m] y[nt][m] over the concatenated rows r of every block.
+// ---------------------------------------------------------------------------------------------
+__global__ void time_shifts_kernel(const float* __restrict__ y, const float* __restrict__ pw,
+                                   const float* __restrict__ pb, float* __restrict__ out, int Nt, int rows, int mod) {
+  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
+  if (warp >= (size_t)Nt * rows) return;
+  const int r = warp % rows, nt = warp / rows;
+  float acc = 0.f;
+  for (int m = threadIdx.x; m < mod; m += 32) acc += pw[(size_t)r * mod + m] * y[(size_t)nt * mod + m];
+  acc = warp_sum(acc);
+  if (threadIdx.x == 0) out[(size_t)nt * rows + r] = acc + pb[r];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight packing: (Cout, Cin, 3, 3) fp32 ->
+//   fwd[tap][chunk][plane][co][kc]  = split(W[co][32 chunk + kc][a][b]),      tap = 3a + b
+//   bwd[tap][chunk][plane][ci][kc]  = split(W[32 chunk + kc][ci][2-a][2-b])   (transposed, flipped:
+//        the input-gradient of a circular stride-1 correlation is the correlation of the cotangent
+//        with this kernel)
+// Rows/K are zero padded to multiples of 16 / 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, bf16* __restrict__ fwd, bf16* __restrict__ bwd,
+                                         int Cout, int Cin) {
+  const int Kf = (Cin + 31) / 32 * 32, Nf = (Cout + 15) / 16 * 16;
+  const int Kb = (Cout + 31) / 32 * 32, Nb = (Cin + 15) / 16 * 16;
+  const size_t nf = (size_t)9 * Kf * Nf, nb = (size_t)9 * Kb * Nb;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (size_t)gridDim.x * blockDim.x) {
+    const bool is_b = i >= nf;
+    size_t j = is_b ? i - nf : i;
+    const int K = is_b ? Kb : Kf, Nn = is_b ? Nb : Nf;
+    const int kc = j % 32;
+    j /= 32;
+    const int row = j % Nn;
+    j /= Nn;
+    const int chunk = j % (K / 32);
+    const int tap = j / (K / 32);
+    const int a = tap / 3, b = tap % 3;
+    const int k = chunk * 32 + kc;
+    float v = 0.f;
+    if (!is_b) {
+      if (row < Cout && k < Cin) v = w[(((size_t)row * Cin + k) * 3 + a) * 3 + b];
+    } else {
+      if (row < Cin && k < Cout) v = w[(((size_t)k * Cin + row) * 3 + (2 - a)) * 3 + (2 - b)];
+    }
+    bf16 hi, lo;
+    split_bf16(v, hi, lo);
+    bf16* dst = is_b ? bwd : fwd;
+    const size_t base = (((size_t)tap * (K / 32) + chunk) * 2) * Nn * 32;
+    dst[base + (size_t)row * 32 + kc] = hi;
+    dst[base + (size_t)Nn * 32 + (size_t)row * 32 + kc] = lo;
+  }
+}
+
+__global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+}  // namespace
+
+int pack_nchw_to_op(const float* x, bf16* op, int N, int Creal, int Cpad, int H, int W, int s2, cudaStream_t st) {
+  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  pack_nchw_kernel<<<grid, block, 0, st>>>(x, op, N, Creal, Cpad, H, W, s2);
+  SDAB_LAUNCH_CHECK("pack_nchw_kernel");
+  return SDAB_OK;
+}
+
+int unpack_f_to_nchw(const float* f, float* x, int N, int Creal, int Cpad, int H, int W, cudaStream_t st) {
+  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  unpack_nchw_kernel<<<grid, block, 0, st>>>(f, x, N, Creal, Cpad, H, W);
+  SDAB_LAUNCH_CHECK("unpack_nchw_kernel");
+  return SDAB_OK;
+}
+
+int f_to_operand(const float* f, bf16* op, int N, int H, int W, int C, int kind, cudaStream_t st) {
+  f_to_operand_kernel<<<warp_grid((size_t)N * H * W), dim3(32, kWarpsPerBlock), 0, st>>>(f, op, N, H, W, C, kind);
+  SDAB_LAUNCH_CHECK("f_to_operand_kernel");
+  return SDAB_OK;
+}
+
+int ln_forward(const float* x, const float* shift, int shift_stride, int Nt, bf16* op, float* rstd, int N, int H, int W,
+               int C, int upsample, cudaStream_t st) {
+  SDAB_REQUIRE(C % 32 == 0 && C <= 512, "LayerNorm channels must be a multiple of 32, at most 512");
+  const dim3 grid = warp_grid((size_t)N * H * W), block(32, kWarpsPerBlock);
+  if (C <= 128)
+    ln_forward_kernel<4><<<grid, block, 0, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample);
+  else if (C <= 256)
+    ln_forward_kernel<8><<<grid, block, 0, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample);
+  else
+    ln_forward_kernel<16><<<grid, block, 0, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample);
+  SDAB_LAUNCH_CHECK("ln_forward_kernel");
+  return SDAB_OK;
+}
+
+int ln_backward(const float* ga, const bf16* a_op, const float* rstd, const float* res, float* gxF, bf16* gxOP, int N,
+                int H, int W, int C, int pooled, cudaStream_t st) {
+  SDAB_REQUIRE(C % 32 == 0 && C <= 512, "LayerNorm channels must be a multiple of 32, at most 512");
+  const dim3 grid = warp_grid((size_t)N * H * W), block(32, kWarpsPerBlock);
+  if (C <= 128)
+    ln_backward_kernel<4><<<grid, block, 0, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled);
+  else if (C <= 256)
+    ln_backward_kernel<8><<<grid, block, 0, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled);
+  else
+    ln_backward_kernel<16><<<grid, block, 0, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled);
+  SDAB_LAUNCH_CHECK("ln_backward_kernel");
+  return SDAB_OK;
+}
+
+int time_shifts(const float* y, const float* pw, const float* pb, float* out, int Nt, int rows, int mod,
+                cudaStream_t st) {
+  time_shifts_kernel<<<warp_grid((size_t)Nt * rows), dim3(32, kWarpsPerBlock), 0, st>>>(y, pw, pb, out, Nt, rows, mod);
+  SDAB_LAUNCH_CHECK("time_shifts_kernel");
+  return SDAB_OK;
+}
+
+int pack_conv_weights(const float* w, bf16* fwd, bf16* bwd, int Cout, int Cin, cudaStream_t st) {
+  pack_conv_weights_kernel<<<296, 256, 0, st>>>(w, fwd, bwd, Cout, Cin);
+  SDAB_LAUNCH_CHECK("pack_conv_weights_kernel");
+  return SDAB_OK;
+}
+
+int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st) {
+  SDAB_CUDA_CHECK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SDAB_OK;
+}
+
+int fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  SDAB_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st));
+  return SDAB_OK;
+}
+
+}  // namespace sdab

@@ -1,0 +1,470 @@
+// unet.cu -- the U-Net schedule: UNet.forward (sda/nn.py:184-206) and its input-gradient as a
+// sequence of conv / LayerNorm launches over internal NHWC tensors (formats in common.cuh).
+//
+// Forward of one modulated residual block (sda/nn.py:27-28, :131-142), per block j at level d:
+//     A_j   = LN_C(x + shift_j)                       ln_forward          -> OP   (saved)
+//     H     = act(conv1(A_j) + b1)                    conv epilogue       -> OP,  C1_j = pre-activation (saved)
+//     x'    = x + conv2(H) + b2                       conv epilogue       -> F
+// Backward (input-gradient only):
+//     gH    = conv2^T(gx')  ;  gC1 = gH * act'(C1_j)  conv epilogue       -> OP
+//     gA    = conv1^T(gC1)                            conv                -> F
+//     gx    = gx' + LN^T(gA; A_j, rstd_j)             ln_backward         -> F + OP
+// Heads (stride 2) read the parity layout; their transpose is a stride-1 conv over the
+// zero-upsampled cotangent.  Tails are LN -> nearest x2 -> conv; their transpose is conv^T -> 2x2
+// sum-pool -> LN^T.
+#include <vector>
+
+#include "common.cuh"
+#include "tile_geom.h"
+
+namespace sdab {
+
+struct ConvLayer {
+  int cin, cout;        // real channels
+  int kf, nf;           // forward GEMM K (ceil32 cin), N (ceil16 cout)
+  int kb, nb;           // backward GEMM K (ceil32 cout), N (ceil16 cin)
+  size_t off_fwd, off_bwd, off_bias;  // byte offsets in the packed buffer
+};
+
+struct Arena {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += round_up_sz(bytes, 1024);
+    return o;
+  }
+};
+
+}  // namespace sdab
+
+using namespace sdab;
+
+struct sdab_unet {
+  sdab_unet_desc d;
+  std::vector<ConvLayer> convs;
+  std::vector<int> block_ch, block_shift_off;
+  int shift_rows = 0;
+  size_t off_projw = 0, off_projb = 0, packed_bytes = 0;
+  uint8_t* packed = nullptr;
+  bool weights_set = false;
+  // indices into convs / blocks
+  std::vector<int> head_conv, tail_conv;                  // per level
+  std::vector<std::vector<int>> desc_c1, asc_c1;          // conv1 index per (level, block); conv2 = +1
+  std::vector<std::vector<int>> desc_blk, asc_blk;        // block ids
+  // saved forward
+  bool saved = false;
+  int sN = 0, sH = 0, sW = 0;
+  void* sws = nullptr;
+};
+
+namespace {
+
+struct Plan {
+  int D;
+  // forward temporaries
+  size_t in_op, shift, finop, outf;
+  std::vector<size_t> x0, x1, skip, hop, xs2, aop_tmp;
+  // saved
+  std::vector<size_t> aop, c1, rstd;  // per block
+  std::vector<size_t> upop, rstd_tail;  // per level (d > 0)
+  // backward temporaries
+  size_t gout_op, gxf;
+  std::vector<size_t> gc1op, gup, gz;
+  size_t total;
+};
+
+size_t f_bytes(int N, int H, int W, int C) { return (size_t)N * H * W * C * sizeof(float); }
+size_t op_bytes(int N, int H, int W, int C) { return OpShape{N, H, W, C, 0}.bytes(); }
+
+Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save) {
+  Plan p;
+  const int D = h->d.depth;
+  p.D = D;
+  Arena a;
+  const int kin0 = round_up(h->d.in_channels, 32), nout = round_up(h->d.out_channels, 16);
+  p.in_op = a.take(op_bytes(N, H, W, kin0));
+  p.shift = a.take((size_t)Nt * h->shift_rows * sizeof(float));
+  p.finop = a.take(op_bytes(N, H, W, h->d.hidden_channels[0]));
+  p.outf = a.take(f_bytes(N, H, W, nout));
+  p.x0.resize(D), p.x1.resize(D), p.skip.resize(D), p.hop.resize(D), p.xs2.resize(D), p.aop_tmp.resize(D);
+  p.upop.assign(D, 0), p.rstd_tail.assign(D, 0), p.gc1op.assign(D, 0), p.gup.assign(D, 0), p.gz.assign(D, 0);
+  for (int d = 0; d < D; ++d) {
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    p.x0[d] = a.take(f_bytes(N, Hd, Wd, C));
+    p.x1[d] = a.take(f_bytes(N, Hd, Wd, C));
+    p.skip[d] = a.take(f_bytes(N, Hd, Wd, C));
+    p.hop[d] = a.take(op_bytes(N, Hd, Wd, C));
+    p.xs2[d] = d < D - 1 ? a.take(op_bytes(N, Hd, Wd, C)) : 0;
+    p.aop_tmp[d] = save ? 0 : a.take(op_bytes(N, Hd, Wd, C));
+    if (d > 0) {
+      p.upop[d] = a.take(op_bytes(N, 2 * Hd, 2 * Wd, C));
+      p.rstd_tail[d] = a.take((size_t)N * Hd * Wd * sizeof(float));
+    }
+  }
+  const int nblk = (int)h->block_ch.size();
+  p.aop.assign(nblk, 0), p.c1.assign(nblk, 0), p.rstd.assign(nblk, 0);
+  if (save) {
+    auto per_level = [&](const std::vector<std::vector<int>>& blk) {
+      for (int d = 0; d < D; ++d) {
+        const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+        for (int j : blk[d]) {
+          p.aop[j] = a.take(op_bytes(N, Hd, Wd, C));
+          p.c1[j] = a.take(f_bytes(N, Hd, Wd, C));
+          p.rstd[j] = a.take((size_t)N * Hd * Wd * sizeof(float));
+        }
+      }
+    };
+    per_level(h->desc_blk);
+    per_level(h->asc_blk);
+    p.gout_op = a.take(op_bytes(N, H, W, round_up(h->d.out_channels, 32)));
+    p.gxf = a.take(f_bytes(N, H, W, round_up(h->d.in_channels, 16)));
+    for (int d = 0; d < D; ++d) {
+      const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+      p.gc1op[d] = a.take(op_bytes(N, Hd, Wd, C));
+      if (d > 0) {
+        p.gup[d] = a.take(f_bytes(N, 2 * Hd, 2 * Wd, C));
+        p.gz[d] = a.take(op_bytes(N, 2 * Hd, 2 * Wd, C));
+      }
+    }
+  } else {
+    p.gout_op = p.gxf = 0;
+  }
+  p.total = a.off;
+  return p;
+}
+
+int check_shape(const sdab_unet* h, int N, int H, int W) {
+  SDAB_REQUIRE(N >= 1, "batch must be positive");
+  const int D = h->d.depth;
+  SDAB_REQUIRE((H % (1 << (D - 1))) == 0 && (W % (1 << (D - 1))) == 0, "H and W must be divisible by 2^(depth-1)");
+  for (int d = 0; d < D; ++d) {
+    TileGeom g;
+    SDAB_TRY(make_tile_geom(N, H >> d, W >> d, g));
+    SDAB_REQUIRE((H >> d) >= 2 && (W >> d) >= 2, "deepest level must be at least 2 x 2");
+  }
+  return SDAB_OK;
+}
+
+int run_conv(int engine, const ConvProblem& p, cudaStream_t st) {
+  return engine == SDAB_ENGINE_SIMT ? conv3x3_simt(p, st) : conv3x3_umma(p, st);
+}
+
+}  // namespace
+
+// ================================================================================== C ABI
+extern "C" {
+
+int sdab_unet_create(const sdab_unet_desc* desc, sdab_unet** out) {
+  SDAB_REQUIRE(desc && out, "null argument");
+  SDAB_REQUIRE(desc->depth >= 1 && desc->depth <= SDAB_MAX_DEPTH, "depth out of range");
+  SDAB_REQUIRE(desc->in_channels >= 1 && desc->in_channels <= 512, "in_channels out of range");
+  SDAB_REQUIRE(desc->out_channels >= 1 && desc->out_channels <= 512, "out_channels out of range");
+  SDAB_REQUIRE(desc->mod_features >= 1, "mod_features must be positive");
+  SDAB_REQUIRE(desc->activation == SDAB_ACT_SILU || desc->activation == SDAB_ACT_RELU,
+               "only SiLU and ReLU activations are implemented");
+  for (int d = 0; d < desc->depth; ++d) {
+    SDAB_REQUIRE(desc->hidden_channels[d] % 32 == 0 && desc->hidden_channels[d] >= 32 &&
+                     desc->hidden_channels[d] <= 512,
+                 "hidden_channels must be multiples of 32 in [32, 512]");
+    SDAB_REQUIRE(desc->hidden_blocks[d] >= 0, "hidden_blocks must be non-negative");
+  }
+  auto* h = new sdab_unet();
+  h->d = *desc;
+  const int D = desc->depth;
+  auto add_conv = [&](int cin, int cout) {
+    ConvLayer c{};
+    c.cin = cin, c.cout = cout;
+    c.kf = round_up(cin, 32), c.nf = round_up(cout, 16);
+    c.kb = round_up(cout, 32), c.nb = round_up(cin, 16);
+    h->convs.push_back(c);
+    return (int)h->convs.size() - 1;
+  };
+  auto add_block = [&](int C) {
+    h->block_ch.push_back(C);
+    h->block_shift_off.push_back(h->shift_rows);
+    h->shift_rows += C;
+    return (int)h->block_ch.size() - 1;
+  };
+  h->head_conv.resize(D), h->tail_conv.resize(D);
+  h->desc_c1.resize(D), h->asc_c1.resize(D), h->desc_blk.resize(D), h->asc_blk.resize(D);
+  for (int d = 0; d < D; ++d) {
+    const int C = desc->hidden_channels[d];
+    h->head_conv[d] = add_conv(d == 0 ? desc->in_channels : desc->hidden_channels[d - 1], C);
+    for (int b = 0; b < desc->hidden_blocks[d]; ++b) {
+      h->desc_c1[d].push_back(add_conv(C, C));
+      add_conv(C, C);
+      h->desc_blk[d].push_back(add_block(C));
+    }
+  }
+  for (int d = D - 1; d >= 0; --d) {
+    const int C = desc->hidden_channels[d];
+    for (int b = 0; b < desc->hidden_blocks[d]; ++b) {
+      h->asc_c1[d].push_back(add_conv(C, C));
+      add_conv(C, C);
+      h->asc_blk[d].push_back(add_block(C));
+    }
+    h->tail_conv[d] = add_conv(C, d == 0 ? desc->out_channels : desc->hidden_channels[d - 1]);
+  }
+  Arena a;
+  for (auto& c : h->convs) {
+    c.off_fwd = a.take((size_t)9 * c.kf * c.nf * 2 * sizeof(bf16));
+    c.off_bwd = a.take((size_t)9 * c.kb * c.nb * 2 * sizeof(bf16));
+    c.off_bias = a.take((size_t)c.nf * sizeof(float));
+  }
+  h->off_projw = a.take((size_t)h->shift_rows * desc->mod_features * sizeof(float));
+  h->off_projb = a.take((size_t)h->shift_rows * sizeof(float));
+  h->packed_bytes = a.off;
+  *out = h;
+  return SDAB_OK;
+}
+
+void sdab_unet_destroy(sdab_unet* h) { delete h; }
+
+int sdab_unet_num_convs(const sdab_unet* h) { return h ? (int)h->convs.size() : 0; }
+int sdab_unet_num_blocks(const sdab_unet* h) { return h ? (int)h->block_ch.size() : 0; }
+
+int sdab_unet_conv_shape(const sdab_unet* h, int i, int* c_out, int* c_in) {
+  SDAB_REQUIRE(h && i >= 0 && i < (int)h->convs.size(), "conv index out of range");
+  if (c_out) *c_out = h->convs[i].cout;
+  if (c_in) *c_in = h->convs[i].cin;
+  return SDAB_OK;
+}
+
+size_t sdab_unet_packed_bytes(const sdab_unet* h) { return h ? h->packed_bytes : 0; }
+
+int sdab_unet_set_weights(sdab_unet* h, const float* const* conv_w, const float* const* conv_b,
+                          const float* const* proj_w, const float* const* proj_b, void* packed, size_t packed_bytes,
+                          void* stream) {
+  SDAB_REQUIRE(h && conv_w && conv_b && proj_w && proj_b && packed, "null argument");
+  SDAB_REQUIRE(packed_bytes >= h->packed_bytes, "packed buffer too small");
+  SDAB_TRY(sdab_device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = (uint8_t*)packed;
+  for (size_t i = 0; i < h->convs.size(); ++i) {
+    const ConvLayer& c = h->convs[i];
+    SDAB_TRY(pack_conv_weights(conv_w[i], (bf16*)(base + c.off_fwd), (bf16*)(base + c.off_bwd), c.cout, c.cin, st));
+    SDAB_TRY(fill_zero(base + c.off_bias, (size_t)c.nf * sizeof(float), st));
+    SDAB_TRY(copy_f32(conv_b[i], (float*)(base + c.off_bias), c.cout, st));
+  }
+  const int mod = h->d.mod_features;
+  for (size_t j = 0; j < h->block_ch.size(); ++j) {
+    const size_t r0 = h->block_shift_off[j];
+    SDAB_TRY(copy_f32(proj_w[j], (float*)(base + h->off_projw) + r0 * mod, (size_t)h->block_ch[j] * mod, st));
+    SDAB_TRY(copy_f32(proj_b[j], (float*)(base + h->off_projb) + r0, h->block_ch[j], st));
+  }
+  h->packed = base;
+  h->weights_set = true;
+  h->saved = false;
+  return SDAB_OK;
+}
+
+size_t sdab_unet_workspace_bytes(const sdab_unet* h, int N, int H, int W, int save) {
+  if (!h || N < 1) return 0;
+  // Nt <= N: size the shift table for the per-sample case
+  return make_plan(h, N, N, H, W, save != 0).total;
+}
+
+int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
+                      void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream) {
+  SDAB_REQUIRE(h && x && y && out && workspace, "null argument");
+  if (!h->weights_set) return fail(SDAB_ERR_STATE, "sdab_unet_set_weights has not been called");
+  SDAB_REQUIRE(Nt == 1 || Nt == N, "the modulation batch must be 1 or N");
+  SDAB_REQUIRE(mode == SDAB_MODE_BF16X3 || mode == SDAB_MODE_BF16, "unknown mode");
+  SDAB_REQUIRE(engine == SDAB_ENGINE_UMMA || engine == SDAB_ENGINE_SIMT, "unknown engine");
+  SDAB_TRY(check_shape(h, N, H, W));
+  SDAB_TRY(sdab_device_check());
+  const Plan p = make_plan(h, N, N, H, W, save != 0);
+  SDAB_REQUIRE(workspace_bytes >= p.total, "workspace too small");
+  SDAB_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
+
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const uint8_t* pk = h->packed;
+  const int D = h->d.depth;
+  const int act = h->d.activation == SDAB_ACT_SILU ? 1 : 2;
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  auto OP = [&](size_t off) { return (bf16*)(ws + off); };
+  auto wf = [&](int ci) { return (const bf16*)(pk + h->convs[ci].off_fwd); };
+  auto bias = [&](int ci) { return (const float*)(pk + h->convs[ci].off_bias); };
+  h->saved = false;
+
+  const int kin0 = round_up(h->d.in_channels, 32);
+  SDAB_TRY(pack_nchw_to_op(x, OP(p.in_op), N, h->d.in_channels, kin0, H, W, 0, st));
+  SDAB_TRY(time_shifts(y, (const float*)(pk + h->off_projw), (const float*)(pk + h->off_projb), F(p.shift), Nt,
+                       h->shift_rows, h->d.mod_features, st));
+
+  // one modulated residual block: cur -> dst (F), optionally also the raw operand of dst
+  auto block = [&](int d, int j, int c1, const float* cur, float* dst, bf16* dst_op) -> int {
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    bf16* aop = save ? OP(p.aop[j]) : OP(p.aop_tmp[d]);
+    SDAB_TRY(ln_forward(cur, F(p.shift) + h->block_shift_off[j], h->shift_rows, Nt, aop,
+                        save ? F(p.rstd[j]) : nullptr, N, Hd, Wd, C, 0, st));
+    ConvProblem q{};
+    q.in = aop, q.wpk = wf(c1), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = C, q.stride = 1, q.mode = mode;
+    q.epi.bias = bias(c1), q.epi.pre = save ? F(p.c1[j]) : nullptr, q.epi.act = act, q.epi.outOP = OP(p.hop[d]);
+    SDAB_TRY(run_conv(engine, q, st));
+    ConvProblem r{};
+    r.in = OP(p.hop[d]), r.wpk = wf(c1 + 1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
+    r.mode = mode;
+    r.epi.bias = bias(c1 + 1), r.epi.res = cur, r.epi.outF = dst, r.epi.outOP = dst_op;
+    return run_conv(engine, r, st);
+  };
+
+  const float* cur = nullptr;
+  for (int d = 0; d < D; ++d) {
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    const int nb = h->d.hidden_blocks[d];
+    {
+      const int ci = h->head_conv[d];
+      ConvProblem q{};
+      q.in = d == 0 ? OP(p.in_op) : OP(p.xs2[d - 1]);
+      q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = h->convs[ci].kf, q.Cout = C, q.stride = d == 0 ? 1 : 2;
+      q.mode = mode, q.epi.bias = bias(ci);
+      q.epi.outF = nb == 0 ? F(p.skip[d]) : F(p.x0[d]);
+      SDAB_TRY(run_conv(engine, q, st));
+      cur = q.epi.outF;
+    }
+    for (int b = 0; b < nb; ++b) {
+      float* dst = b == nb - 1 ? F(p.skip[d]) : (cur == F(p.x0[d]) ? F(p.x1[d]) : F(p.x0[d]));
+      SDAB_TRY(block(d, h->desc_blk[d][b], h->desc_c1[d][b], cur, dst, nullptr));
+      cur = dst;
+    }
+    if (d < D - 1) SDAB_TRY(f_to_operand(cur, OP(p.xs2[d]), N, Hd, Wd, C, 1, st));
+  }
+  for (int d = D - 1; d >= 0; --d) {
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    const int nb = h->d.hidden_blocks[d];
+    bool have_finop = false;
+    for (int b = 0; b < nb; ++b) {
+      float* dst = cur == F(p.x0[d]) ? F(p.x1[d]) : F(p.x0[d]);
+      const bool fin = d == 0 && b == nb - 1;
+      SDAB_TRY(block(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst, fin ? OP(p.finop) : nullptr));
+      have_finop = have_finop || fin;
+      cur = dst;
+    }
+    const int ci = h->tail_conv[d];
+    if (d > 0) {
+      SDAB_TRY(ln_forward(cur, nullptr, 0, 1, OP(p.upop[d]), save ? F(p.rstd_tail[d]) : nullptr, N, Hd, Wd, C, 1, st));
+      ConvProblem q{};
+      q.in = OP(p.upop[d]), q.wpk = wf(ci), q.N = N, q.H = 2 * Hd, q.W = 2 * Wd, q.Cin = C;
+      q.Cout = h->d.hidden_channels[d - 1], q.stride = 1, q.mode = mode;
+      q.epi.bias = bias(ci), q.epi.res = F(p.skip[d - 1]), q.epi.outF = F(p.x0[d - 1]);
+      SDAB_TRY(run_conv(engine, q, st));
+      cur = q.epi.outF;
+    } else {
+      if (!have_finop) SDAB_TRY(f_to_operand(cur, OP(p.finop), N, Hd, Wd, C, 0, st));
+      ConvProblem q{};
+      q.in = OP(p.finop), q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = h->convs[ci].nf;
+      q.stride = 1, q.mode = mode, q.epi.bias = bias(ci), q.epi.outF = F(p.outf);
+      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(unpack_f_to_nchw(F(p.outf), out, N, h->d.out_channels, h->convs[ci].nf, Hd, Wd, st));
+    }
+  }
+  if (save) {
+    h->saved = true;
+    h->sN = N, h->sH = H, h->sW = W, h->sws = workspace;
+  }
+  return SDAB_OK;
+}
+
+int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
+                    int engine, void* stream) {
+  SDAB_REQUIRE(h && gout && gx && workspace, "null argument");
+  if (!h->saved || h->sws != workspace)
+    return fail(SDAB_ERR_STATE, "sdab_unet_dgrad needs a preceding sdab_unet_forward(save=1) on the same workspace");
+  SDAB_REQUIRE(mode == SDAB_MODE_BF16X3 || mode == SDAB_MODE_BF16, "unknown mode");
+  SDAB_REQUIRE(engine == SDAB_ENGINE_UMMA || engine == SDAB_ENGINE_SIMT, "unknown engine");
+  const int N = h->sN, H = h->sH, W = h->sW;
+  const Plan p = make_plan(h, N, N, H, W, true);
+  SDAB_REQUIRE(workspace_bytes >= p.total, "workspace too small");
+
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = (uint8_t*)workspace;
+  const uint8_t* pk = h->packed;
+  const int D = h->d.depth;
+  const int act = h->d.activation == SDAB_ACT_SILU ? 1 : 2;
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  auto OP = [&](size_t off) { return (bf16*)(ws + off); };
+  auto wb = [&](int ci) { return (const bf16*)(pk + h->convs[ci].off_bwd); };
+  // aliases of dead forward temporaries
+  auto G0 = [&](int d) { return F(p.x0[d]); };
+  auto G1 = [&](int d) { return F(p.x1[d]); };
+  auto GA = [&](int d) { return F(p.skip[d]); };
+  auto GOP = [&](int d) { return OP(p.hop[d]); };
+
+  // backward of one block: cur (F, operand in GOP[d]) -> other ping-pong buffer (+ GOP[d])
+  auto block_bwd = [&](int d, int j, int c1, const float* cur, float* dst) -> int {
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    ConvProblem q{};
+    q.in = GOP(d), q.wpk = wb(c1 + 1), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = C, q.stride = 1, q.mode = mode;
+    q.epi.dact = F(p.c1[j]), q.epi.dact_kind = act, q.epi.outOP = OP(p.gc1op[d]);
+    SDAB_TRY(run_conv(engine, q, st));
+    ConvProblem r{};
+    r.in = OP(p.gc1op[d]), r.wpk = wb(c1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
+    r.mode = mode;
+    r.epi.outF = GA(d);
+    SDAB_TRY(run_conv(engine, r, st));
+    return ln_backward(GA(d), OP(p.aop[j]), F(p.rstd[j]), cur, dst, GOP(d), N, Hd, Wd, C, 0, st);
+  };
+
+  const int kout = round_up(h->d.out_channels, 32);
+  SDAB_TRY(pack_nchw_to_op(gout, OP(p.gout_op), N, h->d.out_channels, kout, H, W, 0, st));
+  const float* cur;
+  {
+    const int ci = h->tail_conv[0];
+    ConvProblem q{};
+    q.in = OP(p.gout_op), q.wpk = wb(ci), q.N = N, q.H = H, q.W = W, q.Cin = kout, q.Cout = h->d.hidden_channels[0];
+    q.stride = 1, q.mode = mode, q.epi.outF = G0(0), q.epi.outOP = GOP(0);
+    SDAB_TRY(run_conv(engine, q, st));
+    cur = G0(0);
+  }
+  std::vector<const float*> gskip(D, nullptr);
+  for (int d = 0; d < D; ++d) {  // ascent, reversed
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    for (int b = h->d.hidden_blocks[d] - 1; b >= 0; --b) {
+      float* dst = cur == G0(d) ? G1(d) : G0(d);
+      SDAB_TRY(block_bwd(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst));
+      cur = dst;
+    }
+    if (d < D - 1) {
+      gskip[d] = cur;
+      const int ci = h->tail_conv[d + 1];
+      const int Cn = h->d.hidden_channels[d + 1];
+      ConvProblem q{};
+      q.in = GOP(d), q.wpk = wb(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
+      q.epi.outF = F(p.gup[d + 1]);
+      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(ln_backward(F(p.gup[d + 1]), OP(p.upop[d + 1]), F(p.rstd_tail[d + 1]), nullptr, G0(d + 1), GOP(d + 1), N,
+                           Hd / 2, Wd / 2, Cn, 1, st));
+      cur = G0(d + 1);
+    }
+  }
+  for (int d = D - 1; d >= 0; --d) {  // descent, reversed
+    const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    for (int b = h->d.hidden_blocks[d] - 1; b >= 0; --b) {
+      float* dst = cur == G0(d) ? G1(d) : G0(d);
+      SDAB_TRY(block_bwd(d, h->desc_blk[d][b], h->desc_c1[d][b], cur, dst));
+      cur = dst;
+    }
+    const int ci = h->head_conv[d];
+    if (d > 0) {
+      const int Cp = h->d.hidden_channels[d - 1];
+      SDAB_TRY(f_to_operand(cur, OP(p.gz[d]), N, 2 * Hd, 2 * Wd, C, 2, st));
+      float* dst = gskip[d - 1] == G0(d - 1) ? G1(d - 1) : G0(d - 1);
+      ConvProblem q{};
+      q.in = OP(p.gz[d]), q.wpk = wb(ci), q.N = N, q.H = 2 * Hd, q.W = 2 * Wd, q.Cin = C, q.Cout = Cp, q.stride = 1;
+      q.mode = mode, q.epi.res = gskip[d - 1], q.epi.outF = dst, q.epi.outOP = GOP(d - 1);
+      SDAB_TRY(run_conv(engine, q, st));
+      cur = dst;
+    } else {
+      ConvProblem q{};
+      q.in = GOP(0), q.wpk = wb(ci), q.N = N, q.H = H, q.W = W, q.Cin = C, q.Cout = h->convs[ci].nb, q.stride = 1;
+      q.mode = mode, q.epi.outF = F(p.gxf);
+      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(unpack_f_to_nchw(F(p.gxf), gx, N, h->d.in_channels, h->convs[ci].nb, H, W, st));
+    }
+  }
+  return SDAB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,464 @@
+r"""Neural networks -- drop-in for ``sda.nn`` (reference: /root/reference/sda/nn.py).
+
+Same class names, constructor arguments, ``forward`` signatures and ``state_dict``
+keys as the reference.  ``UNet`` keeps its parameters in ordinary ``nn.Conv2d`` /
+``nn.Linear`` modules (so ``load_state_dict``, ``.cuda()`` and optimizers work) but,
+for the Kolmogorov configuration (2-D, kernel 3, stride 2, circular padding --
+experiments/kolmogorov/utils.py:59-68), ``forward`` runs the whole network through
+libsdab: hand-written sm_100a kernels behind the C ABI of ``include/sdab.h``.
+That path has no fallback: CPU tensors, non-sm_100 devices or a missing library
+raise.
+
+Configurations outside the hot path (1-D U-Net of the Lorenz global score,
+``ResMLP``; SURVEY.md section 8a rows a6 and config 1 "plumbing, no GPU") are plain
+PyTorch by design and never touch the library.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Callable, Sequence, Union
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from . import _lib
+
+__all__ = ['LayerNorm', 'ResidualBlock', 'ModResidualBlock', 'ResMLP', 'UNet']
+
+
+class LayerNorm(nn.Module):
+    r"""Standardisation over `dim`, unbiased variance, no affine parameters.
+
+    Restates ``zuko.nn.LayerNorm`` (zuko 0.1.4), imported by the reference at
+    sda/nn.py:8 and used at :61, :137, :163.
+    """
+
+    def __init__(self, dim: Union[int, Sequence[int]] = -1, eps: float = 1e-5):
+        super().__init__()
+
+        self.dim = dim if isinstance(dim, int) else tuple(dim)
+        self.eps = eps
+
+    def forward(self, x: Tensor) -> Tensor:
+        variance, mean = torch.var_mean(x, dim=self.dim, keepdim=True)
+
+        return (x - mean) / (variance + self.eps).sqrt()
+
+    def extra_repr(self) -> str:
+        return f'dim={self.dim}'
+
+
+class ResidualBlock(nn.Sequential):
+    r"""x + f(x).  Reference: sda/nn.py:11-15."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x + super().forward(x)
+
+
+class ModResidualBlock(nn.Module):
+    r"""x + residue(x + project(y)).  Reference: sda/nn.py:18-28."""
+
+    def __init__(self, project: nn.Module, residue: nn.Module):
+        super().__init__()
+
+        self.project = project
+        self.residue = residue
+
+    def forward(self, x: Tensor, y: Tensor) -> Tensor:
+        return x + self.residue(x + self.project(y))
+
+
+class ResMLP(nn.Sequential):
+    r"""Residual MLP (plain PyTorch; Lorenz plumbing).  Reference: sda/nn.py:31-71."""
+
+    def __init__(
+        self,
+        in_features: int,
+        out_features: int,
+        hidden_features: Sequence[int] = (64, 64),
+        activation: Callable[[], nn.Module] = nn.ReLU,
+        **kwargs,
+    ):
+        layers = []
+        widths = [in_features, *hidden_features, out_features]
+
+        for before, after in zip(widths[:-1], widths[1:]):
+            if after != before:
+                layers.append(nn.Linear(before, after, **kwargs))
+
+            layers.append(
+                ResidualBlock(
+                    LayerNorm(),
+                    nn.Linear(after, after, **kwargs),
+                    activation(),
+                    nn.Linear(after, after, **kwargs),
+                )
+            )
+
+        super().__init__(*layers)
+
+        self.in_features = in_features
+        self.out_features = out_features
+
+
+_ACTIVATION_CODES = {nn.SiLU: _lib.ACT_SILU, nn.ReLU: _lib.ACT_RELU}
+
+
+def _mode() -> int:
+    r"""Arithmetic mode of the tensor-core convolutions (env SDAB_MODE: bf16x3 | bf16)."""
+
+    name = os.environ.get('SDAB_MODE', 'bf16x3').lower()
+
+    if name not in ('bf16x3', 'bf16'):
+        raise ValueError(f'SDAB_MODE must be bf16x3 or bf16, not {name}')
+
+    return _lib.MODE_BF16X3 if name == 'bf16x3' else _lib.MODE_BF16
+
+
+def _engine() -> int:
+    name = os.environ.get('SDAB_ENGINE', 'umma').lower()
+
+    if name not in ('umma', 'simt'):
+        raise ValueError(f'SDAB_ENGINE must be umma or simt, not {name}')
+
+    return _lib.ENGINE_UMMA if name == 'umma' else _lib.ENGINE_SIMT
+
+
+class _RaiseOnBackward(torch.autograd.Function):
+    r"""Identity whose backward raises: gradients w.r.t. the modulation vector (hence
+    w.r.t. any parameter) are a next-tier row, and must not be
+    silently dropped."""
+
+    @staticmethod
+    def forward(ctx, y):
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError(
+            'sda_b200.nn.UNet computes input gradients only (guided sampling); parameter / '
+            'modulation gradients (training, SURVEY.md section 8f) are not implemented yet'
+        )
+
+
+class _UNetFunction(torch.autograd.Function):
+    r"""UNet.forward / input-VJP through libsdab (sdab_unet_forward / sdab_unet_dgrad)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, y: Tensor, net: 'UNet') -> Tensor:
+        save = bool(ctx.needs_input_grad[0])
+        out = net._native_forward(x, y, save)
+        ctx.net = net
+        ctx.save = save
+        ctx.y_shape = y.shape
+        ctx.token = net._forward_token
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        net = ctx.net
+
+        if not ctx.save:
+            return None, None, None
+
+        if ctx.token != net._forward_token:
+            raise RuntimeError(
+                'sda_b200.nn.UNet: backward through a forward pass whose saved activations were '
+                'overwritten by a later forward of the same module'
+            )
+
+        gx = net._native_dgrad(g)
+        gy = g.new_zeros(ctx.y_shape) if ctx.needs_input_grad[1] else None
+
+        return gx, gy, None
+
+
+class UNet(nn.Module):
+    r"""U-Net with additive time modulation.  Reference: sda/nn.py:74-206.
+
+    Arguments are the reference's: `in_channels, out_channels, mod_features,
+    hidden_channels, hidden_blocks, kernel_size, stride, activation, spatial` and
+    `**kwargs` forwarded to the convolutions (e.g. `padding_mode='circular'`).
+    """
+
+    def __init__(
+        self,
+        in_channels: int,
+        out_channels: int,
+        mod_features: int,
+        hidden_channels: Sequence[int] = (32, 64, 128),
+        hidden_blocks: Sequence[int] = (2, 3, 5),
+        kernel_size: Union[int, Sequence[int]] = 3,
+        stride: Union[int, Sequence[int]] = 2,
+        activation: Callable[[], nn.Module] = nn.ReLU,
+        spatial: int = 2,
+        **kwargs,
+    ):
+        super().__init__()
+
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.spatial = spatial
+
+        conv = {1: nn.Conv1d, 2: nn.Conv2d, 3: nn.Conv3d}[spatial]
+        ks = [kernel_size] * spatial if isinstance(kernel_size, int) else list(kernel_size)
+        st = [stride] * spatial if isinstance(stride, int) else list(stride)
+        kwargs.update(kernel_size=ks, padding=[k // 2 for k in ks])
+
+        def block(c: int) -> ModResidualBlock:
+            return ModResidualBlock(
+                project=nn.Sequential(nn.Linear(mod_features, c), nn.Unflatten(-1, (-1,) + (1,) * spatial)),
+                residue=nn.Sequential(LayerNorm(-(spatial + 1)), conv(c, c, **kwargs), activation(), conv(c, c, **kwargs)),
+            )
+
+        heads, tails, descent, ascent = [], [], [], []
+
+        for i, n in enumerate(hidden_blocks):
+            c = hidden_channels[i]
+
+            if i == 0:
+                heads.append(conv(in_channels, c, **kwargs))
+                tails.append(conv(c, out_channels, **kwargs))
+            else:
+                below = hidden_channels[i - 1]
+                heads.append(nn.Sequential(conv(below, c, stride=st, **kwargs)))
+                tails.append(
+                    nn.Sequential(
+                        LayerNorm(-(spatial + 1)),
+                        nn.Upsample(scale_factor=tuple(st), mode='nearest'),
+                        conv(c, below, **kwargs),
+                    )
+                )
+
+            descent.append(nn.ModuleList(block(c) for _ in range(n)))
+            ascent.append(nn.ModuleList(block(c) for _ in range(n)))
+
+        # same registration order and naming as the reference (state_dict compatibility)
+        self.heads = nn.ModuleList(heads)
+        self.tails = nn.ModuleList(reversed(tails))
+        self.descent = nn.ModuleList(descent)
+        self.ascent = nn.ModuleList(reversed(ascent))
+
+        # ---- native path bookkeeping (not part of the state_dict)
+        act_code = _ACTIVATION_CODES.get(activation if isinstance(activation, type) else type(activation()))
+        self._native = (
+            spatial == 2
+            and ks == [3, 3]
+            and st == [2, 2]
+            and kwargs.get('padding_mode', 'zeros') == 'circular'
+            and act_code is not None
+            and all(c % 32 == 0 and 32 <= c <= 512 for c in hidden_channels)
+            and len(hidden_channels) == len(hidden_blocks) <= _lib.MAX_DEPTH
+            and kwargs.get('bias', True)
+            and kwargs.get('dilation', 1) in (1, [1, 1], (1, 1))
+            and kwargs.get('groups', 1) == 1
+        )
+        self._desc = (in_channels, out_channels, mod_features, tuple(hidden_channels), tuple(hidden_blocks), act_code)
+        self._handle = None
+        self._packed = None
+        self._packed_key = None
+        self._workspace = None
+        self._forward_token = 0
+
+    # ------------------------------------------------------------------ reference module-tree forward
+    def _module_forward(self, x: Tensor, y: Tensor) -> Tensor:
+        r"""Literal module-tree evaluation (sda/nn.py:184-206) for configurations outside the
+        native path (1-D / non-circular U-Nets of the Lorenz experiments)."""
+
+        memory = []
+
+        for head, blocks in zip(self.heads, self.descent):
+            x = head(x)
+
+            for blk in blocks:
+                x = blk(x, y)
+
+            memory.append(x)
+
+        memory.pop()
+
+        for blocks, tail in zip(self.ascent, self.tails):
+            for blk in blocks:
+                x = blk(x, y)
+
+            x = tail(x) + memory.pop() if memory else tail(x)
+
+        return x
+
+    # ------------------------------------------------------------------ native path
+    def _ordered_parameters(self):
+        r"""Parameters in the library's canonical order (include/sdab.h: sdab_unet_set_weights)."""
+
+        D = len(self.heads)
+        convs, projs = [], []
+
+        def add_blocks(mods):
+            for blk in mods:
+                convs.extend((blk.residue[1], blk.residue[3]))
+                projs.append(blk.project[0])
+
+        for d in range(D):
+            convs.append(self.heads[d] if d == 0 else self.heads[d][0])
+            add_blocks(self.descent[d])
+
+        for i in range(D):  # ascent[i] / tails[i]: i = 0 is the deepest level
+            add_blocks(self.ascent[i])
+            convs.append(self.tails[i][2] if i < D - 1 else self.tails[i])
+
+        return convs, projs
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+
+        for k in ('_handle', '_packed', '_packed_key', '_workspace'):
+            state[k] = None
+
+        return state
+
+    def _ensure_handle(self, device: torch.device):
+        lib = _lib.load()
+
+        if self._handle is None:
+            in_c, out_c, mod, channels, blocks, act = self._desc
+            desc = _lib.UNetDesc()
+            desc.in_channels, desc.out_channels, desc.mod_features = in_c, out_c, mod
+            desc.depth = len(channels)
+
+            for i, (c, b) in enumerate(zip(channels, blocks)):
+                desc.hidden_channels[i] = c
+                desc.hidden_blocks[i] = b
+
+            desc.activation = act
+            handle = ctypes.c_void_p()
+            _lib.check(lib.sdab_unet_create(ctypes.byref(desc), ctypes.byref(handle)))
+            self._handle = handle
+
+        convs, projs = self._ordered_parameters()
+        params = [p for m in convs + projs for p in (m.weight, m.bias)]
+        key = (device, tuple((p.data_ptr(), p._version) for p in params))
+
+        if key != self._packed_key:
+            for p in params:
+                if p.device != device or p.dtype != torch.float32:
+                    raise RuntimeError('sda_b200.nn.UNet: parameters must be float32 on the same CUDA device as the input')
+
+            assert len(convs) == lib.sdab_unet_num_convs(self._handle)
+            assert len(projs) == lib.sdab_unet_num_blocks(self._handle)
+
+            nbytes = lib.sdab_unet_packed_bytes(self._handle)
+
+            if self._packed is None or self._packed.numel() < nbytes or self._packed.device != device:
+                self._packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+            def ptrs(tensors):
+                # .contiguous() copies must outlive the call: keep them in `keep`
+                arr = (ctypes.c_void_p * len(tensors))()
+                keep = []
+                for i, t in enumerate(tensors):
+                    t = t.detach().contiguous()
+                    keep.append(t)
+                    arr[i] = t.data_ptr()
+                return arr, keep
+
+            cw, k1 = ptrs([m.weight for m in convs])
+            cb, k2 = ptrs([m.bias for m in convs])
+            pw, k3 = ptrs([m.weight for m in projs])
+            pb, k4 = ptrs([m.bias for m in projs])
+            _lib.check(
+                lib.sdab_unet_set_weights(
+                    self._handle, cw, cb, pw, pb, self._packed.data_ptr(), self._packed.numel(), _lib.stream_ptr()
+                )
+            )
+            del k1, k2, k3, k4
+            self._packed_key = key
+
+        return lib
+
+    def _get_workspace(self, lib, N: int, H: int, W: int, save: bool, device) -> Tensor:
+        nbytes = lib.sdab_unet_workspace_bytes(self._handle, N, H, W, int(save))
+
+        if nbytes == 0:
+            raise RuntimeError('sda_b200.nn.UNet: invalid workspace query')
+
+        ws = self._workspace
+
+        if ws is None or ws.numel() < nbytes + 1024 or ws.device != device:
+            self._workspace = None
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self._workspace = ws
+
+        return ws
+
+    def _native_forward(self, x: Tensor, y: Tensor, save: bool) -> Tensor:
+        if not x.is_cuda:
+            raise RuntimeError(
+                'sda_b200.nn.UNet: the 2-D circular U-Net runs on sm_100 CUDA devices only (no CPU fallback); '
+                f'got a tensor on {x.device}'
+            )
+
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise RuntimeError(f'expected input of shape (N, {self.in_channels}, H, W), got {tuple(x.shape)}')
+
+        with torch.cuda.device(x.device):
+            lib = self._ensure_handle(x.device)
+            x = x.detach().to(torch.float32).contiguous()
+            y = y.detach().to(torch.float32).reshape(-1, y.shape[-1]).contiguous()
+            N, _, H, W = x.shape
+            Nt = y.shape[0]
+
+            if Nt not in (1, N):
+                raise RuntimeError(f'the modulation batch ({Nt}) must be 1 or match the input batch ({N})')
+
+            ws = self._get_workspace(lib, N, H, W, save, x.device)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            out = torch.empty((N, self.out_channels, H, W), dtype=torch.float32, device=x.device)
+            self._forward_token += 1
+            self._saved_mode = (_mode(), _engine())
+            _lib.check(
+                lib.sdab_unet_forward(
+                    self._handle, x.data_ptr(), y.data_ptr(), Nt, N, H, W, out.data_ptr(), base,
+                    ws.numel() - (base - ws.data_ptr()), int(save), self._saved_mode[0], self._saved_mode[1],
+                    _lib.stream_ptr(),
+                )
+            )
+
+        return out
+
+    def _native_dgrad(self, g: Tensor) -> Tensor:
+        with torch.cuda.device(g.device):
+            lib = _lib.load()
+            g = g.detach().to(torch.float32).contiguous()
+            N, _, H, W = g.shape
+            ws = self._workspace
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            gx = torch.empty((N, self.in_channels, H, W), dtype=torch.float32, device=g.device)
+            _lib.check(
+                lib.sdab_unet_dgrad(
+                    self._handle, g.data_ptr(), gx.data_ptr(), base, ws.numel() - (base - ws.data_ptr()),
+                    self._saved_mode[0], self._saved_mode[1], _lib.stream_ptr(),
+                )
+            )
+
+        return gx
+
+    def forward(self, x: Tensor, y: Tensor) -> Tensor:
+        if not self._native:
+            return self._module_forward(x, y)
+
+        if torch.is_grad_enabled() and y.requires_grad:
+            y = _RaiseOnBackward.apply(y)
+
+        return _UNetFunction.apply(x, y, self)
+
+    def __del__(self):
+        handle = getattr(self, '_handle', None)
+
+        if handle is not None:
+            try:
+                _lib.load().sdab_unet_destroy(handle)
+            except Exception:
+                pass

@@ -1,0 +1,120 @@
+r"""Window sharding of the Markov-blanket score over the GPUs of one box.
+
+The reference has no distributed code; its long-trajectory
+scaling is algorithmic: the score of a trajectory is composed from independent window
+scores (sda/score.py:134-144).  That independence is the data-parallel axis used here:
+
+* one process per GPU (torchrun), every rank holds the full trajectory `x`, advances
+  it with the same counter-based Philox noise, and therefore stays bit-identical;
+* per score evaluation each rank runs the U-Net on a contiguous range of the
+  flattened (B, L - 2k) windows, then ONE all-gather (NCCL over NVLink / NVSwitch)
+  rebuilds the full window-score tensor;
+* when the evaluation is differentiated (GaussianScore), the backward pass runs the
+  input-VJP of the local windows only and all-gathers the window input-gradients;
+  the overlap-add that follows (`unfold` adjoint) is local and in fixed order, so
+  the result does not depend on the number of ranks.
+
+`shard_windows(score)` switches a `MCScoreNet` to this mode; nothing else changes for
+the caller.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from .score import MCScoreNet
+
+
+def window_range(n_windows: int, rank: int, world: int):
+    r"""Contiguous range [begin, end) of flattened windows owned by `rank`, and the padded
+    per-rank count (equal on all ranks, as all_gather needs)."""
+
+    per = -(-n_windows // world)
+    begin = min(rank * per, n_windows)
+    end = min(begin + per, n_windows)
+
+    return begin, end, per
+
+
+class _ShardedKernel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xw: Tensor, kernel, t: Tensor, c: Optional[Tensor], group) -> Tensor:
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        B, nw = xw.shape[:2]
+        flat = xw.reshape(B * nw, *xw.shape[2:])
+        begin, end, per = window_range(B * nw, rank, world)
+        local = flat[begin:end]
+        need_grad = ctx.needs_input_grad[0]
+
+        if end > begin:
+            if need_grad:
+                with torch.enable_grad():
+                    local = local.detach().requires_grad_(True)
+                    out_local = kernel(local.unsqueeze(0), t, c).squeeze(0)
+            else:
+                out_local = kernel(local.unsqueeze(0), t, c).squeeze(0)
+        else:
+            out_local = flat.new_zeros((0,) + tuple(flat.shape[1:]))
+
+        ctx.saved = (local, out_local) if need_grad else None
+        ctx.meta = (B, nw, begin, end, per, group, tuple(flat.shape[1:]))
+
+        return _gather(out_local.detach(), per, B * nw, group).reshape(xw.shape)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        B, nw, begin, end, per, group, tail = ctx.meta
+        local, out_local = ctx.saved
+        g_local = g.reshape(B * nw, *tail)[begin:end]
+
+        if end > begin:
+            (gx_local,) = torch.autograd.grad(out_local, local, g_local.contiguous())
+        else:
+            gx_local = g.new_zeros((0,) + tail)
+
+        gx = _gather(gx_local, per, B * nw, group).reshape(g.shape)
+
+        return gx, None, None, None, None
+
+
+def _gather(local: Tensor, per: int, total: int, group) -> Tensor:
+    r"""all-gather of equally padded shards; returns the first `total` rows."""
+
+    world = dist.get_world_size(group)
+    padded = local.new_zeros((per,) + tuple(local.shape[1:]))
+    padded[: local.shape[0]] = local
+    out = local.new_empty((world * per,) + tuple(local.shape[1:]))
+    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
+
+    return out[:total]
+
+
+class ShardedMCScoreNet(MCScoreNet):
+    r"""`MCScoreNet` whose kernel evaluations are sharded over `group` (see module docstring)."""
+
+    shard_group = None
+
+    def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.shard_group) == 1 or t.dim() > 0:
+            return super().forward(x, t, c)
+
+        xw = self.unfold(x, self.order)
+        s = _ShardedKernel.apply(xw, self.kernel, t, c, self.shard_group)
+
+        return self.fold(s, self.order)
+
+
+def shard_windows(score: MCScoreNet, group=None) -> MCScoreNet:
+    r"""Switches `score` (in place) to window-sharded evaluation over `group`."""
+
+    if not isinstance(score, MCScoreNet):
+        raise TypeError('shard_windows expects a MCScoreNet')
+
+    score.__class__ = ShardedMCScoreNet
+    score.shard_group = group
+
+    return score

@@ -1,0 +1,501 @@
+r"""Score modules -- drop-in for ``sda.score`` (reference: /root/reference/sda/score.py).
+
+Same classes, constructor arguments and call signatures as the reference.  What
+changes is where the arithmetic runs:
+
+* ``MCScoreNet``    window unfold / fold and their adjoints are libsdab kernels
+                    (sdab_unfold_cat, sdab_fold, sdab_fold_transpose,
+                    sdab_unfold_transpose_add) wrapped in autograd Functions;
+* ``ScoreUNet``     its ``network`` is ``sda_b200.nn.UNet`` (tcgen05 convolutions);
+* ``VPSDE.sample``  schedule scalars are computed once on the host, the predictor and
+                    corrector updates are single fused kernels with a counter-based
+                    Philox stream (identical on every rank);
+* ``GaussianScore`` the Tweedie estimate is a fused kernel with an analytic adjoint;
+                    the user's observation operator ``A`` stays ordinary PyTorch.
+
+On CPU tensors (Lorenz plumbing) the window maps, sampler and
+guidance run the reference's plain PyTorch formulas; the 2-D U-Net itself never
+runs on the CPU.
+"""
+
+from __future__ import annotations
+
+import math
+import os
+from typing import Callable, Optional, Union
+
+import torch
+import torch.nn as nn
+from torch import Size, Tensor
+
+from . import _lib
+from .nn import *  # noqa: F401,F403  (the reference re-exports sda.nn from sda.score)
+from .nn import ResMLP, UNet
+
+try:  # progress bar as in the reference (sda/score.py:250); optional here
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    tqdm = None
+
+
+def broadcast(*tensors: Tensor, ignore: Union[int, list] = 0):
+    r"""Broadcasts all but the last `ignore` dimensions (zuko.utils.broadcast, used at
+    sda/score.py:57,60,87)."""
+
+    if isinstance(ignore, int):
+        ignore = [ignore] * len(tensors)
+
+    dims = [t.dim() - i for t, i in zip(tensors, ignore)]
+    common = torch.broadcast_shapes(*(t.shape[:d] for t, d in zip(tensors, dims)))
+
+    return [torch.broadcast_to(t, common + t.shape[d:]) for t, d in zip(tensors, dims)]
+
+
+class TimeEmbedding(nn.Sequential):
+    r"""cos/sin features of pi * (1..16) * t through a 2-layer MLP.  Reference: sda/score.py:15-35."""
+
+    def __init__(self, features: int):
+        super().__init__(nn.Linear(32, 256), nn.SiLU(), nn.Linear(256, features))
+
+        self.register_buffer('freqs', torch.pi * torch.arange(1, 16 + 1))
+
+    def forward(self, t: Tensor) -> Tensor:
+        t = self.freqs * t.unsqueeze(dim=-1)
+        t = torch.cat((t.cos(), t.sin()), dim=-1)
+
+        return super().forward(t)
+
+
+class ScoreNet(nn.Module):
+    r"""MLP score network (Lorenz plumbing, plain PyTorch).  Reference: sda/score.py:38-63."""
+
+    def __init__(self, features: int, context: int = 0, embedding: int = 16, **kwargs):
+        super().__init__()
+
+        self.embedding = TimeEmbedding(embedding)
+        self.network = ResMLP(features + context + embedding, features, **kwargs)
+
+    def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        t = self.embedding(t)
+        parts = (x, t) if c is None else (x, t, c)
+
+        return self.network(torch.cat(broadcast(*parts, ignore=1), dim=-1))
+
+
+class ScoreUNet(nn.Module):
+    r"""U-Net score network.  Reference: sda/score.py:66-93.
+
+    Subclassable exactly like the reference's (experiments/kolmogorov/utils.py:29-46
+    overrides `forward` and registers a `forcing` buffer).
+    """
+
+    def __init__(self, channels: int, context: int = 0, embedding: int = 64, **kwargs):
+        super().__init__()
+
+        self.embedding = TimeEmbedding(embedding)
+        self.network = UNet(channels + context, channels, embedding, **kwargs)
+
+    def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        dims = self.network.spatial + 1
+
+        if c is None:
+            y = x
+        else:
+            y = torch.cat(broadcast(x, c, ignore=dims), dim=-dims)
+
+        y = y.reshape(-1, *y.shape[-dims:])
+        t = self.embedding(t.reshape(-1))
+
+        return self.network(y, t).reshape(x.shape)
+
+
+class MCScoreWrapper(nn.Module):
+    r"""Disguises a `ScoreUNet` over time as a Markov-chain score.  Reference: sda/score.py:96-110."""
+
+    def __init__(self, score: nn.Module):
+        super().__init__()
+
+        self.score = score
+
+    def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        return self.score(x.transpose(1, 2), t, c).transpose(1, 2)
+
+
+# --------------------------------------------------------------------------- window maps
+def _is_native(x: Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 5
+
+
+class _Unfold(torch.autograd.Function):
+    r"""(B, L, C, H, W) -> (B, L-2k, (2k+1) C, H, W), materialised by sdab_unfold_cat;
+    backward = deterministic overlap-add (sdab_unfold_transpose_add)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, order: int) -> Tensor:
+        B, L, C, H, W = x.shape
+        ctx.dims = (B, L, C, H, W, order)
+        x = x.contiguous()
+        out = torch.empty((B, L - 2 * order, (2 * order + 1) * C, H, W), dtype=x.dtype, device=x.device)
+
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sdab_unfold_cat(x.data_ptr(), None, out.data_ptr(), B, L, C, 0, H, W, order, _lib.stream_ptr()))
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        B, L, C, H, W, order = ctx.dims
+        g = g.contiguous()
+        gx = torch.empty((B, L, C, H, W), dtype=g.dtype, device=g.device)
+
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().sdab_unfold_transpose_add(g.data_ptr(), gx.data_ptr(), B, L, C, 0, H, W, order, _lib.stream_ptr()))
+
+        return gx, None
+
+
+class _Fold(torch.autograd.Function):
+    r"""(B, L-2k, (2k+1) C, H, W) -> (B, L, C, H, W) by sdab_fold; backward = sdab_fold_transpose."""
+
+    @staticmethod
+    def forward(ctx, s: Tensor, order: int) -> Tensor:
+        B, nw, CH, H, W = s.shape
+        C = CH // (2 * order + 1)
+        L = nw + 2 * order
+        ctx.dims = (B, L, C, H, W, order)
+        s = s.contiguous()
+        out = torch.empty((B, L, C, H, W), dtype=s.dtype, device=s.device)
+
+        with torch.cuda.device(s.device):
+            _lib.check(_lib.load().sdab_fold(s.data_ptr(), out.data_ptr(), B, L, C, H, W, order, _lib.stream_ptr()))
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        B, L, C, H, W, order = ctx.dims
+        g = g.contiguous()
+        gs = torch.empty((B, L - 2 * order, (2 * order + 1) * C, H, W), dtype=g.dtype, device=g.device)
+
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().sdab_fold_transpose(g.data_ptr(), gs.data_ptr(), B, L, C, H, W, order, _lib.stream_ptr()))
+
+        return gs, None
+
+
+class MCScoreNet(nn.Module):
+    r"""Score of a Markov chain composed from window scores.  Reference: sda/score.py:113-164.
+
+    `window_range = (begin, end)` (optional attribute, default all) restricts the evaluated
+    windows to a contiguous range: the hook used by `sda_b200.parallel` to shard windows over GPUs.
+    """
+
+    def __init__(self, features: int, context: int = 0, order: int = 1, **kwargs):
+        super().__init__()
+
+        self.order = order
+
+        if kwargs.get('spatial', 0) > 0:
+            build = ScoreUNet
+        else:
+            build = ScoreNet
+
+        self.kernel = build(features * (2 * order + 1), context, **kwargs)
+
+    def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        x = self.unfold(x, self.order)
+        s = self.kernel(x, t, c)
+        s = self.fold(s, self.order)
+
+        return s
+
+    @staticmethod
+    def unfold(x: Tensor, order: int) -> Tensor:
+        if order >= 1 and _is_native(x):
+            if x.shape[1] < 2 * order + 1:
+                raise RuntimeError(
+                    f'maximum size for tensor at dimension 1 is {x.shape[1]} but size is {2 * order + 1}'
+                )
+
+            return _Unfold.apply(x, order)
+
+        # reference formula (zero-copy view), sda/score.py:148-153
+        return x.unfold(1, 2 * order + 1, 1).movedim(-1, 2).flatten(2, 3)
+
+    @staticmethod
+    def fold(x: Tensor, order: int) -> Tensor:
+        if order >= 1 and _is_native(x) and x.shape[2] % (2 * order + 1) == 0:
+            return _Fold.apply(x, order)
+
+        # reference formula, sda/score.py:157-164
+        x = x.unflatten(2, (2 * order + 1, -1))
+
+        return torch.cat((x[:, 0, :order], x[:, :, order], x[:, -1, -order:]), dim=1)
+
+
+# --------------------------------------------------------------------------- VPSDE
+class VPSDE(nn.Module):
+    r"""Variance-preserving SDE noise schedule, sampler and loss.  Reference: sda/score.py:167-276.
+
+    mu(t) = alpha(t), sigma(t)^2 = 1 - alpha(t)^2 + eta^2.
+    """
+
+    def __init__(self, eps: nn.Module, shape: Size, alpha: str = 'cos', eta: float = 1e-3):
+        super().__init__()
+
+        self.eps = eps
+        self.shape = shape
+        self.dims = tuple(range(-len(shape), 0))
+        self.eta = eta
+
+        if alpha == 'lin':
+            self.alpha = lambda t: 1 - (1 - eta) * t
+        elif alpha == 'cos':
+            self.alpha = lambda t: torch.cos(math.acos(math.sqrt(eta)) * t) ** 2
+        elif alpha == 'exp':
+            self.alpha = lambda t: torch.exp(math.log(eta) * t**2)
+        else:
+            raise ValueError()
+
+        self.register_buffer('device', torch.empty(()))
+
+        # test hook: callable(x) -> z replacing the corrector's Philox draw (noise injection)
+        self.noise_source: Optional[Callable[[Tensor], Tensor]] = None
+
+    def mu(self, t: Tensor) -> Tensor:
+        return self.alpha(t)
+
+    def sigma(self, t: Tensor) -> Tensor:
+        return (1 - self.alpha(t) ** 2 + self.eta**2).sqrt()
+
+    def forward(self, x: Tensor, t: Tensor, train: bool = False) -> Tensor:
+        r"""Samples from the perturbation kernel p(x(t) | x)."""
+
+        t = t.reshape(t.shape + (1,) * len(self.shape))
+
+        eps = torch.randn_like(x)
+        x = self.mu(t) * x + self.sigma(t) * eps
+
+        if train:
+            return x, eps
+        else:
+            return x
+
+    def sample(
+        self,
+        shape: Size = (),
+        c: Tensor = None,
+        steps: int = 64,
+        corrections: int = 0,
+        tau: float = 1.0,
+    ) -> Tensor:
+        r"""Predictor-corrector sampling of p(x(0)).  Reference: sda/score.py:225-263."""
+
+        shape = tuple(shape)
+        device = self.device.device
+
+        # initial noise drawn on the CPU then moved, as the reference does (score.py:243)
+        x = torch.randn(shape + tuple(self.shape)).to(self.device)
+        x = x.reshape(-1, *self.shape).contiguous()
+
+        time = torch.linspace(1, 0, steps + 1).to(self.device)
+        dt = 1 / steps
+
+        # schedule scalars once, on the host, in the reference's fp32 arithmetic
+        time_host = torch.linspace(1, 0, steps + 1).to(self.device.dtype)
+        mu_t, mu_n = self.mu(time_host), self.mu(time_host - dt)
+        sg_t, sg_n = self.sigma(time_host), self.sigma(time_host - dt)
+        ratio = mu_n / mu_t
+        coef = sg_n - ratio * sg_t
+
+        native = x.is_cuda and x.dtype == torch.float32
+        iterator = range(steps)
+
+        if tqdm is not None and not os.environ.get('SDAB_NO_TQDM'):
+            iterator = tqdm(iterator, ncols=88)
+
+        if native:
+            lib = _lib.load()
+            B = x.shape[0]
+            scratch = torch.empty(lib.sdab_vpsde_correct_scratch_floats(B), dtype=torch.float32, device=device)
+            seed = int(torch.randint(0, 2**62, (), dtype=torch.int64))  # from torch's CPU generator
+            draws = 0
+
+        with torch.no_grad():
+            for i in iterator:
+                t = time[i]
+
+                # Predictor
+                eps = self.eps(x, t, c)
+
+                if native:
+                    eps = eps.contiguous()
+
+                    with torch.cuda.device(device):
+                        _lib.check(lib.sdab_vpsde_predict(x.data_ptr(), eps.data_ptr(), float(ratio[i]), float(coef[i]), x.numel(), _lib.stream_ptr()))
+                else:
+                    x = ratio[i] * x + coef[i] * eps
+
+                # Corrector
+                for _ in range(corrections):
+                    if native:
+                        z = self.noise_source(x).contiguous() if self.noise_source is not None else None
+                        eps = self.eps(x, t - dt, c).contiguous()
+
+                        with torch.cuda.device(device):
+                            _lib.check(
+                                lib.sdab_vpsde_correct(
+                                    x.data_ptr(), eps.data_ptr(), None if z is None else z.data_ptr(), float(tau),
+                                    float(sg_n[i]), seed, draws * ((x.numel() + 3) // 4 + B), B, x.numel(),
+                                    scratch.data_ptr(), _lib.stream_ptr(),
+                                )
+                            )
+
+                        draws += 1
+                    else:
+                        z = self.noise_source(x) if self.noise_source is not None else torch.randn_like(x)
+                        eps = self.eps(x, t - dt, c)
+                        delta = tau / eps.square().mean(dim=self.dims, keepdim=True)
+
+                        x = x - (delta * eps + torch.sqrt(2 * delta) * z) * sg_n[i]
+
+        return x.reshape(shape + tuple(self.shape))
+
+    def loss(self, x: Tensor, c: Tensor = None, w: Tensor = None) -> Tensor:
+        r"""Denoising loss.  Reference: sda/score.py:265-276."""
+
+        t = torch.rand(x.shape[0], dtype=x.dtype, device=x.device)
+        x, eps = self.forward(x, t, train=True)
+
+        err = (self.eps(x, t, c) - eps).square()
+
+        if w is None:
+            return err.mean()
+        else:
+            return (err * w).mean() / w.mean()
+
+
+class SubVPSDE(VPSDE):
+    r"""sigma(t) = 1 - alpha(t)^2 + eta.  Reference: sda/score.py:279-288."""
+
+    def sigma(self, t: Tensor) -> Tensor:
+        return 1 - self.alpha(t) ** 2 + self.eta
+
+
+class SubSubVPSDE(VPSDE):
+    r"""sigma(t) = 1 - alpha(t) + eta.  Reference: sda/score.py:291-300."""
+
+    def sigma(self, t: Tensor) -> Tensor:
+        return 1 - self.alpha(t) + self.eta
+
+
+# --------------------------------------------------------------------------- guidance
+class _Tweedie(torch.autograd.Function):
+    r"""x_hat = (x - sigma eps) / mu as one kernel (sdab_tweedie) with its analytic adjoint."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, eps: Tensor, mu: float, sigma: float) -> Tensor:
+        ctx.coef = (mu, sigma)
+        x, eps = x.contiguous(), eps.contiguous()
+        out = torch.empty_like(x)
+
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sdab_tweedie(x.data_ptr(), eps.data_ptr(), mu, sigma, out.data_ptr(), x.numel(), _lib.stream_ptr()))
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        mu, sigma = ctx.coef
+        gx = g / mu if ctx.needs_input_grad[0] else None
+        ge = g * (-sigma / mu) if ctx.needs_input_grad[1] else None
+
+        return gx, ge, None, None
+
+
+def _tweedie(x: Tensor, eps: Tensor, mu: Tensor, sigma: Tensor) -> Tensor:
+    if x.is_cuda and x.dtype == torch.float32 and eps.shape == x.shape and mu.dim() == 0 and sigma.dim() == 0:
+        return _Tweedie.apply(x, eps, float(mu), float(sigma))
+
+    return (x - sigma * eps) / mu
+
+
+class DPSGaussianScore(nn.Module):
+    r"""Diffusion posterior sampling guidance.  Reference: sda/score.py:303-344.
+
+    Returns -sigma(t) s(x(t), t | y).  The signature `forward(x, t)` is the reference's (it
+    does not accept the context that `VPSDE.sample` passes; kept as is).
+    """
+
+    def __init__(self, y: Tensor, A: Callable[[Tensor], Tensor], sde: VPSDE, zeta: float = 1.0):
+        super().__init__()
+
+        self.register_buffer('y', y)
+
+        self.A = A
+        self.sde = sde
+        self.zeta = zeta
+
+    def forward(self, x: Tensor, t: Tensor) -> Tensor:
+        mu, sigma = self.sde.mu(t), self.sde.sigma(t)
+
+        with torch.enable_grad():
+            x = x.detach().requires_grad_(True)
+
+            eps = self.sde.eps(x, t)
+            x_ = _tweedie(x, eps, mu, sigma)
+            err = (self.y - self.A(x_)).square().sum()
+
+        (s,) = torch.autograd.grad(err, x)
+        s = -s * self.zeta / err.sqrt()
+
+        return eps - sigma * s
+
+
+class GaussianScore(nn.Module):
+    r"""Likelihood guidance for p(y | x) = N(y | A(x), Sigma).  Reference: sda/score.py:347-396.
+
+    Returns -sigma(t) s(x(t), t | y).
+    """
+
+    def __init__(
+        self,
+        y: Tensor,
+        A: Callable[[Tensor], Tensor],
+        std: Union[float, Tensor],
+        sde: VPSDE,
+        gamma: Union[float, Tensor] = 1e-2,
+        detach: bool = False,
+    ):
+        super().__init__()
+
+        self.register_buffer('y', y)
+        self.register_buffer('std', torch.as_tensor(std))
+        self.register_buffer('gamma', torch.as_tensor(gamma))
+
+        self.A = A
+        self.sde = sde
+        self.detach = detach
+
+    def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        mu, sigma = self.sde.mu(t), self.sde.sigma(t)
+
+        if self.detach:
+            eps = self.sde.eps(x, t, c)
+
+        with torch.enable_grad():
+            x = x.detach().requires_grad_(True)
+
+            if not self.detach:
+                eps = self.sde.eps(x, t, c)
+
+            x_ = _tweedie(x, eps, mu, sigma)
+
+            err = self.y - self.A(x_)
+            var = self.std**2 + self.gamma * (sigma / mu) ** 2
+
+            log_p = -(err**2 / var).sum() / 2
+
+        (s,) = torch.autograd.grad(log_p, x)
+
+        return (eps - sigma * s).detach()
