@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+r"""Headline benchmark: denoising steps/sec of guided posterior sampling on synthetic Kolmogorov
+256 x 256, L = 64 trajectories (BASELINE.json `metric`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One denoising step = one iteration of the loop of VPSDE.sample (reference sda/score.py:250-261) =
+1 predictor + 1 corrector update = 2 guided score evaluations, each a U-Net forward AND
+input-gradient over all 60 trajectory windows (GaussianScore, score.py:375-396).
+Network = experiments/kolmogorov/train.py CONFIG (window 5, channels 96/192/384, blocks 3/3/3,
+SiLU, circular padding) at 256 x 256 with random-init weights; observation = every 4th frame
+coarsened x8 (experiments/kolmogorov/figures.ipynb:204), std 0.1, gamma 1e-2, tau 0.5.
+
+Multi-GPU: the window batch is sharded over the ranks (strong scaling: the trajectory is fixed), one
+all-gather of window scores (and of window input-gradients in the backward) per evaluation.
+
+`--impl reference` times the CPU restatement of the reference algorithm (oracle/score_oracle.py, plain
+PyTorch ATen ops with all host threads -- the reference itself is pure PyTorch and does not travel
+to the GPU box) on a bounded sample of the same workload.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault('SDAB_NO_TQDM', '1')
+
+import torch  # noqa: E402
+
+WINDOW, CHANNELS, BLOCKS = 5, (96, 192, 384), (3, 3, 3)
+SIZE, LENGTH = 256, 64
+SCHEDULE_STEPS, CORRECTIONS, TAU = 256, 1, 0.5
+CONV_FLOP_PER_PIXEL = 6_837_696  # forward conv FLOPs per output pixel and window
+
+
+# ------------------------------------------------------------------------------------ model
+def make_score(size: int, device):
+    r"""make_score / LocalScoreUNet of experiments/kolmogorov/utils.py:29-70 on this repo's classes."""
+
+    import sda_b200.score as sc
+
+    class LocalScoreUNet(sc.ScoreUNet):
+        def __init__(self, channels, size=64, **kwargs):
+            super().__init__(channels, 1, **kwargs)
+            domain = 2 * torch.pi / size * (torch.arange(size) + 1 / 2)
+            self.register_buffer('forcing', torch.sin(4 * domain).expand(1, size, size).clone())
+
+        def forward(self, x, t, c=None):
+            return super().forward(x, t, self.forcing)
+
+    torch.manual_seed(0)
+    score = sc.MCScoreNet(2, order=WINDOW // 2)
+    score.kernel = LocalScoreUNet(
+        WINDOW * 2, size, embedding=64, hidden_channels=CHANNELS, hidden_blocks=BLOCKS, kernel_size=3,
+        activation=torch.nn.SiLU, spatial=2, padding_mode='circular',
+    )
+
+    return score.to(device)
+
+
+def observation(v):
+    r"""A(x): every 4th frame, coarsened x8 (figures.ipynb:204)."""
+
+    from sda_b200.mcs import KolmogorovFlow
+
+    return KolmogorovFlow.coarsen(v[:, ::4], 8)
+
+
+def synthetic(batch: int, length: int, size: int):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((batch, length, 2, size, size), generator=g)
+    y = torch.randn((batch, (length + 3) // 4, 2, size // 8, size // 8), generator=g)
+    return x, y
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits', '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([f.strip() for f in line.split(',')])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 9]
+
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+
+        sm = sorted(float(r[1]) for r in rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for j, n in enumerate(names) if any(r[5 + j].lower().startswith('active') for r in rows)]
+
+        return {'sm_mhz': sm[len(sm) // 2], 'sm_max_mhz': float(rows[0][2]), 'reasons': reasons, 'samples': len(rows),
+                'power_w_max': max(float(r[3]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------ CPU baseline
+def cpu_step_seconds(n_steps: int, warm: int):
+    r"""Seconds per denoising step of the oracle (reference algorithm, torch CPU, all host threads) on a
+    ONE-window slice (L = 5) of the 256 x 256 workload.  Returns (seconds per sample step, cores)."""
+
+    from oracle import score_oracle as so
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    score = make_score(SIZE, 'cpu')
+    state = {k[len('kernel.'):]: v for k, v in score.state_dict().items()}
+    k = WINDOW // 2
+    x, y = synthetic(1, WINDOW, SIZE)
+    eps_fn = lambda a, b: so.gaussian_score(lambda c, d: so.mc_score(state, c, d, k), y, observation, 0.1, a, b, gamma=1e-2)  # noqa: E731
+    g = torch.Generator().manual_seed(1)
+    noise = [torch.randn(x.shape, generator=g) for _ in range((n_steps + warm) * CORRECTIONS)]
+    times = []
+
+    for i in range(n_steps + warm):
+        t0 = time.perf_counter()
+        # one loop iteration at schedule position i (cost does not depend on i)
+        so.pc_sample(eps_fn, x, steps=SCHEDULE_STEPS, corrections=CORRECTIONS, tau=TAU,
+                     noise=noise[i * CORRECTIONS:(i + 1) * CORRECTIONS], n_steps=1)
+        times.append(time.perf_counter() - t0)
+
+    timed = times[warm:]
+
+    return sum(timed) / len(timed), cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+
+    windows = LENGTH - 2 * (WINDOW // 2)
+    sec, cores = cpu_step_seconds(args.steps, args.warmup)
+    value = 1.0 / (sec * windows)
+    sample = (f'one denoising step (2 guided score evaluations, U-Net forward + input-gradient) on a 1-window slice '
+              f'(L={WINDOW}) of the {SIZE}x{SIZE} workload, scaled x{windows} windows')
+    print(json.dumps({
+        'impl': 'reference',
+        'metric': 'denoising steps/sec, Kolmogorov 256x256 L=64 guided posterior sampling',
+        'value': value, 'unit': 'steps/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 / value, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 1),
+        'cpu_baseline': {'value': value, 'unit': 'steps/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def workload_config(args, world):
+    return {
+        'workload': f'Kolmogorov {SIZE}x{SIZE}, L={LENGTH}, B={args.batch}, window {WINDOW} (k=2) -> {args.batch * (LENGTH - 4)} windows; '
+                    f'U-Net {CHANNELS} x {BLOCKS}; guided (GaussianScore, detach=False), corrections={CORRECTIONS}, tau={TAU}',
+        'windows': args.batch * (LENGTH - 4),
+        'score_evaluations_per_step': 1 + CORRECTIONS,
+        'parallelism': f'window-sharded x{world}' if world > 1 else 'single GPU',
+        'mode': os.environ.get('SDAB_MODE', 'bf16x3'),
+        'l2': 'per-step working set (tens of GB of activations) exceeds the 126 MB L2; no explicit flush needed',
+    }
+
+
+# ------------------------------------------------------------------------------------ ours
+def run_ours(args, rank, local_rank, world):
+    import ctypes
+
+    import torch.distributed as dist
+
+    import sda_b200.score as sc
+    from sda_b200 import _lib
+    from sda_b200.parallel import shard_windows
+
+    device = torch.device('cuda', local_rank)
+    torch.cuda.set_device(device)
+
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+
+    lib = _lib.load()
+    score = make_score(SIZE, device)
+
+    if world > 1:
+        shard_windows(score)
+
+    x_host, y_host = synthetic(args.batch, LENGTH, SIZE)
+    x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
+    guided = sc.GaussianScore(y_host.to(device), A=observation, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2).to(device)
+    sde = sc.VPSDE(guided, shape=tuple(x_host.shape[1:])).to(device)
+    x = x_host.to(device)
+    state = sde.sampler_state(x, SCHEDULE_STEPS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        tv = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        return float(tv)
+
+    step = 0
+
+    for _ in range(args.warmup):
+        x = sde.denoise_step(x, step, state, corrections=CORRECTIONS, tau=TAU)
+        step += 1
+
+    # ---------------- device-resident timed region
+    sampler = ClockSampler(local_rank)
+
+    if rank == 0:
+        sampler.start()
+
+    barrier()
+    _lib.launch_count(reset=True)
+    lib.sdab_conv_profile(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+
+    for _ in range(args.steps):
+        x = sde.denoise_step(x, step, state, corrections=CORRECTIONS, tau=TAU)
+        step += 1
+
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count()
+    conv_ms, conv_flops, conv_launches = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    _lib.check(lib.sdab_conv_profile_read(ctypes.byref(conv_ms), ctypes.byref(conv_flops), ctypes.byref(conv_launches)))
+    lib.sdab_conv_profile(0)
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(x).all(), 'non-finite state after the timed steps'
+
+    # ---------------- end to end through the public step API, host buffers in and out
+    barrier()
+    t0 = time.perf_counter()
+
+    for _ in range(args.steps):
+        x.copy_(x_pin, non_blocking=True)
+        guided.y.copy_(y_pin, non_blocking=True)
+        x = sde.denoise_step(x, step % SCHEDULE_STEPS, state, corrections=CORRECTIONS, tau=TAU)
+        x_pin.copy_(x, non_blocking=True)
+        torch.cuda.synchronize()
+        step += 1
+
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_file = ROOT / 'MEASURED_PEAKS.json'
+    peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)'
+    peak = 1400.0
+
+    if peaks_file.exists():
+        peak = float(json.loads(peaks_file.read_text()).get('bf16_tflops_sustained', peak))
+    else:
+        peak_src = 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
+
+    achieved = conv_flops.value / (conv_ms.value * 1e-3) / 1e12 if conv_ms.value > 0 else 0.0
+    passes = 3 if os.environ.get('SDAB_MODE', 'bf16x3') == 'bf16x3' else 1
+    traffic = None
+    traffic_file = ROOT / 'profiles' / 'conv_umma_traffic.json'
+
+    if traffic_file.exists():
+        traffic = json.loads(traffic_file.read_text()).get('dram_bytes_per_launch')
+
+    value = args.steps / (ms * 1e-3)
+    out = {
+        'metric': 'denoising steps/sec, Kolmogorov 256x256 L=64 guided posterior sampling',
+        'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
+        'dtype': 'bf16x3 (split-bf16 operands, fp32 accumulate)' if passes == 3 else 'bf16 (fp32 accumulate)',
+        'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
+        'e2e': {'value': args.steps / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': x_pin.numel() * 4 + y_pin.numel() * 4,
+                'd2h_bytes_per_step': x_pin.numel() * 4},
+        'gpu_launches': int(launches),
+        'roofline': {
+            'bound': 'tensor', 'kernel': 'conv_umma_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+            'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+            'note': f'algorithmic FLOPs (one multiply-add pair per product) over CUDA-event kernel time of {conv_launches.value} '
+                    f'launches on rank 0; the {passes}-pass mode issues {passes}x that many tensor-core FLOPs '
+                    f'(tensor-pipe fraction ~ {passes * achieved / peak:.3f})',
+            'conv_share_of_step': conv_ms.value / ms,
+        },
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        sec, cores = cpu_step_seconds(2, 0)
+        windows = LENGTH - 2 * (WINDOW // 2)
+        out['cpu_baseline'] = {
+            'value': 1.0 / (sec * windows * args.batch), 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+            'sample': f'2 denoising steps of the torch-CPU oracle on a 1-window slice (L={WINDOW}) at {SIZE}x{SIZE}, '
+                      f'{sec:.1f} s each, scaled x{windows * args.batch} windows',
+        }
+
+    print(json.dumps(out))
+
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=1, help='trajectories sampled together (B)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    if args.impl == 'reference':
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

@@ -117,6 +117,11 @@ int sdab_conv3x3(const float* x, const float* weight, const float* bias, float* 
                  int W, int stride, int transpose, int mode, int engine, void* workspace, size_t workspace_bytes,
                  void* stream);
 
+/* Per-launch device timing of the convolution engine (CUDA events on the launching stream):
+ * enable, run, then read the summed kernel time (ms), algorithmic FLOPs and launch count. */
+int sdab_conv_profile(int enable);
+int sdab_conv_profile_read(double* ms, double* flops, long long* launches);
+
 /* Number of kernels launched by this library on the calling thread since the last reset. */
 long long sdab_launch_count(int reset);
 

@@ -38,6 +38,8 @@ _PROTOTYPES = {
     'sdab_version': (c_int, []),
     'sdab_device_check': (c_int, []),
     'sdab_launch_count': (c_longlong, [c_int]),
+    'sdab_conv_profile': (c_int, [c_int]),
+    'sdab_conv_profile_read': (c_int, [POINTER(c_double), POINTER(c_double), POINTER(c_longlong)]),
     # U-Net
     'sdab_unet_create': (c_int, [POINTER(UNetDesc), POINTER(c_void_p)]),
     'sdab_unet_destroy': (None, [c_void_p]),

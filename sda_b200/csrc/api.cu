@@ -1,4 +1,6 @@
 // api.cu -- error reporting, device check and launch accounting of libsdab.
+#include <vector>
+
 #include "common.cuh"
 
 namespace sdab {
@@ -17,6 +19,38 @@ int fail(int code, const std::string& msg) {
 
 void count_launch(int n) { g_launches += n; }
 
+// ---- optional per-launch timing of the convolution engine (bench.py's live roofline)
+namespace {
+struct ConvProfiler {
+  bool enabled = false;
+  std::vector<cudaEvent_t> events;  // pairs (begin, end)
+  size_t used = 0;
+  double flops = 0.0;
+  long long launches = 0;
+};
+thread_local ConvProfiler g_prof;
+}  // namespace
+
+void conv_profile_before(cudaStream_t st) {
+  if (!g_prof.enabled) return;
+  if (g_prof.used + 2 > g_prof.events.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      g_prof.events.push_back(e);
+    }
+  }
+  cudaEventRecord(g_prof.events[g_prof.used], st);
+}
+
+void conv_profile_after(cudaStream_t st, double flops) {
+  if (!g_prof.enabled) return;
+  cudaEventRecord(g_prof.events[g_prof.used + 1], st);
+  g_prof.used += 2;
+  g_prof.flops += flops;
+  g_prof.launches += 1;
+}
+
 }  // namespace sdab
 
 extern "C" {
@@ -29,6 +63,29 @@ long long sdab_launch_count(int reset) {
   const long long v = sdab::g_launches;
   if (reset) sdab::g_launches = 0;
   return v;
+}
+
+int sdab_conv_profile(int enable) {
+  sdab::g_prof.enabled = enable != 0;
+  sdab::g_prof.used = 0;
+  sdab::g_prof.flops = 0.0;
+  sdab::g_prof.launches = 0;
+  return SDAB_OK;
+}
+
+int sdab_conv_profile_read(double* ms, double* flops, long long* launches) {
+  double total = 0.0;
+  for (size_t i = 0; i + 1 < sdab::g_prof.used; i += 2) {
+    if (cudaEventSynchronize(sdab::g_prof.events[i + 1]) != cudaSuccess)
+      return sdab::fail(SDAB_ERR_DEVICE, "cudaEventSynchronize failed while reading the conv profile");
+    float t = 0.f;
+    cudaEventElapsedTime(&t, sdab::g_prof.events[i], sdab::g_prof.events[i + 1]);
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (flops) *flops = sdab::g_prof.flops;
+  if (launches) *launches = sdab::g_prof.launches;
+  return SDAB_OK;
 }
 
 int sdab_device_check(void) {

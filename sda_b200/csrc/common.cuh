@@ -26,6 +26,8 @@ namespace sdab {
 void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 void count_launch(int n = 1);
+void conv_profile_before(cudaStream_t st);
+void conv_profile_after(cudaStream_t st, double flops);
 
 #define SDAB_CUDA_CHECK(expr)                                                                      \
   do {                                                                                             \
@@ -128,6 +130,7 @@ struct ConvProblem {
   int Cin, Cout;       // padded: Cin % 32 == 0, Cout % 16 == 0
   int stride;          // 1 or 2
   int mode;            // SDAB_MODE_*
+  double flops;        // algorithmic FLOPs of this launch (2 * pixels * 9 * C_in,real * C_out,real), for profiling
   ConvEpilogue epi;
 };
 

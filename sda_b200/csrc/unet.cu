@@ -145,8 +145,15 @@ int check_shape(const sdab_unet* h, int N, int H, int W) {
   return SDAB_OK;
 }
 
-int run_conv(int engine, const ConvProblem& p, cudaStream_t st) {
-  return engine == SDAB_ENGINE_SIMT ? conv3x3_simt(p, st) : conv3x3_umma(p, st);
+// cr_in, cr_out: real (unpadded) channel counts when they differ from the padded GEMM sizes;
+// scale: fraction of the dense taps that are algorithmically needed (1/4 for the zero-upsampled
+// transpose of a stride-2 head) -- both only feed the algorithmic FLOP count of the profiler.
+int run_conv(int engine, ConvProblem p, cudaStream_t st, int cr_in = -1, int cr_out = -1, double scale = 1.0) {
+  p.flops = scale * 2.0 * 9.0 * (double)p.N * p.H * p.W * (cr_in < 0 ? p.Cin : cr_in) * (cr_out < 0 ? p.Cout : cr_out);
+  conv_profile_before(st);
+  const int s = engine == SDAB_ENGINE_SIMT ? conv3x3_simt(p, st) : conv3x3_umma(p, st);
+  conv_profile_after(st, p.flops);
+  return s;
 }
 
 }  // namespace
@@ -321,7 +328,7 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = h->convs[ci].kf, q.Cout = C, q.stride = d == 0 ? 1 : 2;
       q.mode = mode, q.epi.bias = bias(ci);
       q.epi.outF = nb == 0 ? F(p.skip[d]) : F(p.x0[d]);
-      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(run_conv(engine, q, st, h->convs[ci].cin));
       cur = q.epi.outF;
     }
     for (int b = 0; b < nb; ++b) {
@@ -356,7 +363,7 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       ConvProblem q{};
       q.in = OP(p.finop), q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = h->convs[ci].nf;
       q.stride = 1, q.mode = mode, q.epi.bias = bias(ci), q.epi.outF = F(p.outf);
-      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(run_conv(engine, q, st, -1, h->d.out_channels));
       SDAB_TRY(unpack_f_to_nchw(F(p.outf), out, N, h->d.out_channels, h->convs[ci].nf, Hd, Wd, st));
     }
   }
@@ -415,7 +422,7 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
     ConvProblem q{};
     q.in = OP(p.gout_op), q.wpk = wb(ci), q.N = N, q.H = H, q.W = W, q.Cin = kout, q.Cout = h->d.hidden_channels[0];
     q.stride = 1, q.mode = mode, q.epi.outF = G0(0), q.epi.outOP = GOP(0);
-    SDAB_TRY(run_conv(engine, q, st));
+    SDAB_TRY(run_conv(engine, q, st, h->d.out_channels));
     cur = G0(0);
   }
   std::vector<const float*> gskip(D, nullptr);
@@ -454,13 +461,13 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       ConvProblem q{};
       q.in = OP(p.gz[d]), q.wpk = wb(ci), q.N = N, q.H = 2 * Hd, q.W = 2 * Wd, q.Cin = C, q.Cout = Cp, q.stride = 1;
       q.mode = mode, q.epi.res = gskip[d - 1], q.epi.outF = dst, q.epi.outOP = GOP(d - 1);
-      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(run_conv(engine, q, st, -1, -1, 0.25));
       cur = dst;
     } else {
       ConvProblem q{};
       q.in = GOP(0), q.wpk = wb(ci), q.N = N, q.H = H, q.W = W, q.Cin = C, q.Cout = h->convs[ci].nb, q.stride = 1;
       q.mode = mode, q.epi.outF = F(p.gxf);
-      SDAB_TRY(run_conv(engine, q, st));
+      SDAB_TRY(run_conv(engine, q, st, -1, h->d.in_channels));
       SDAB_TRY(unpack_f_to_nchw(F(p.gxf), gx, N, h->d.in_channels, h->convs[ci].nb, H, W, st));
     }
   }

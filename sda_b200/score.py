@@ -292,74 +292,96 @@ class VPSDE(nn.Module):
         r"""Predictor-corrector sampling of p(x(0)).  Reference: sda/score.py:225-263."""
 
         shape = tuple(shape)
-        device = self.device.device
 
         # initial noise drawn on the CPU then moved, as the reference does (score.py:243)
         x = torch.randn(shape + tuple(self.shape)).to(self.device)
         x = x.reshape(-1, *self.shape).contiguous()
 
-        time = torch.linspace(1, 0, steps + 1).to(self.device)
-        dt = 1 / steps
-
-        # schedule scalars once, on the host, in the reference's fp32 arithmetic
-        time_host = torch.linspace(1, 0, steps + 1).to(self.device.dtype)
-        mu_t, mu_n = self.mu(time_host), self.mu(time_host - dt)
-        sg_t, sg_n = self.sigma(time_host), self.sigma(time_host - dt)
-        ratio = mu_n / mu_t
-        coef = sg_n - ratio * sg_t
-
-        native = x.is_cuda and x.dtype == torch.float32
+        state = self.sampler_state(x, steps)
         iterator = range(steps)
 
         if tqdm is not None and not os.environ.get('SDAB_NO_TQDM'):
             iterator = tqdm(iterator, ncols=88)
 
-        if native:
-            lib = _lib.load()
-            B = x.shape[0]
-            scratch = torch.empty(lib.sdab_vpsde_correct_scratch_floats(B), dtype=torch.float32, device=device)
-            seed = int(torch.randint(0, 2**62, (), dtype=torch.int64))  # from torch's CPU generator
-            draws = 0
-
-        with torch.no_grad():
-            for i in iterator:
-                t = time[i]
-
-                # Predictor
-                eps = self.eps(x, t, c)
-
-                if native:
-                    eps = eps.contiguous()
-
-                    with torch.cuda.device(device):
-                        _lib.check(lib.sdab_vpsde_predict(x.data_ptr(), eps.data_ptr(), float(ratio[i]), float(coef[i]), x.numel(), _lib.stream_ptr()))
-                else:
-                    x = ratio[i] * x + coef[i] * eps
-
-                # Corrector
-                for _ in range(corrections):
-                    if native:
-                        z = self.noise_source(x).contiguous() if self.noise_source is not None else None
-                        eps = self.eps(x, t - dt, c).contiguous()
-
-                        with torch.cuda.device(device):
-                            _lib.check(
-                                lib.sdab_vpsde_correct(
-                                    x.data_ptr(), eps.data_ptr(), None if z is None else z.data_ptr(), float(tau),
-                                    float(sg_n[i]), seed, draws * ((x.numel() + 3) // 4 + B), B, x.numel(),
-                                    scratch.data_ptr(), _lib.stream_ptr(),
-                                )
-                            )
-
-                        draws += 1
-                    else:
-                        z = self.noise_source(x) if self.noise_source is not None else torch.randn_like(x)
-                        eps = self.eps(x, t - dt, c)
-                        delta = tau / eps.square().mean(dim=self.dims, keepdim=True)
-
-                        x = x - (delta * eps + torch.sqrt(2 * delta) * z) * sg_n[i]
+        for i in iterator:
+            x = self.denoise_step(x, i, state, c=c, corrections=corrections, tau=tau)
 
         return x.reshape(shape + tuple(self.shape))
+
+    def sampler_state(self, x: Tensor, steps: int) -> dict:
+        r"""Per-run constants of the sampling loop: the time grid (device), the schedule scalars
+        (computed once on the host in the reference's fp32 arithmetic, score.py:252-253) and the
+        Philox stream of the corrector noise."""
+
+        dt = 1 / steps
+        time_host = torch.linspace(1, 0, steps + 1).to(self.device.dtype)
+        mu_t, mu_n = self.mu(time_host), self.mu(time_host - dt)
+        sg_t, sg_n = self.sigma(time_host), self.sigma(time_host - dt)
+        ratio = mu_n / mu_t
+        state = {
+            'dt': dt,
+            'time': torch.linspace(1, 0, steps + 1).to(x.device),
+            'ratio': ratio,
+            'coef': sg_n - ratio * sg_t,
+            'sigma_next': sg_n,
+            'native': x.is_cuda and x.dtype == torch.float32,
+            'draws': 0,
+        }
+
+        if state['native']:
+            lib = _lib.load()
+            state['scratch'] = torch.empty(
+                lib.sdab_vpsde_correct_scratch_floats(x.shape[0]), dtype=torch.float32, device=x.device
+            )
+            state['seed'] = int(torch.randint(0, 2**62, (), dtype=torch.int64))  # torch's CPU generator
+
+        return state
+
+    def denoise_step(self, x: Tensor, i: int, state: dict, c: Tensor = None, corrections: int = 0, tau: float = 1.0) -> Tensor:
+        r"""One iteration of the sampling loop (score.py:250-261): predictor + `corrections` Langevin
+        corrections, i.e. (1 + corrections) score evaluations.  On CUDA `x` is updated in place."""
+
+        dt, t = state['dt'], state['time'][i]
+        ratio, coef, sigma_next = state['ratio'][i], state['coef'][i], state['sigma_next'][i]
+
+        with torch.no_grad():
+            # Predictor
+            eps = self.eps(x, t, c)
+
+            if state['native']:
+                lib = _lib.load()
+                B = x.shape[0]
+                eps = eps.contiguous()
+
+                with torch.cuda.device(x.device):
+                    _lib.check(lib.sdab_vpsde_predict(x.data_ptr(), eps.data_ptr(), float(ratio), float(coef), x.numel(), _lib.stream_ptr()))
+            else:
+                x = ratio * x + coef * eps
+
+            # Corrector
+            for _ in range(corrections):
+                if state['native']:
+                    z = self.noise_source(x).contiguous() if self.noise_source is not None else None
+                    eps = self.eps(x, t - dt, c).contiguous()
+
+                    with torch.cuda.device(x.device):
+                        _lib.check(
+                            lib.sdab_vpsde_correct(
+                                x.data_ptr(), eps.data_ptr(), None if z is None else z.data_ptr(), float(tau),
+                                float(sigma_next), state['seed'], state['draws'] * ((x.numel() + 3) // 4 + B), B,
+                                x.numel(), state['scratch'].data_ptr(), _lib.stream_ptr(),
+                            )
+                        )
+
+                    state['draws'] += 1
+                else:
+                    z = self.noise_source(x) if self.noise_source is not None else torch.randn_like(x)
+                    eps = self.eps(x, t - dt, c)
+                    delta = tau / eps.square().mean(dim=self.dims, keepdim=True)
+
+                    x = x - (delta * eps + torch.sqrt(2 * delta) * z) * sigma_next
+
+        return x
 
     def loss(self, x: Tensor, c: Tensor = None, w: Tensor = None) -> Tensor:
         r"""Denoising loss.  Reference: sda/score.py:265-276."""

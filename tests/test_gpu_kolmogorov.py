@@ -1,0 +1,88 @@
+r"""Kolmogorov stepper on the GPU against the NumPy oracle (parity unpinned by the reference, see
+oracle/kolmogorov_oracle.py) and through the invariants of the scheme.  fp32 tolerance: 1e-4
+relative L2 on one transition (82 inner steps at 256 x 256) against the fp64 oracle."""
+
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kolmogorov_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('size', [64, 256])
+def test_transition_matches_oracle(size):
+    from sda_b200.mcs import KolmogorovFlow
+
+    chain = KolmogorovFlow(size=size, dt=0.2)
+    assert chain.steps == ko.inner_steps(size, 0.2)
+    x0 = ko.prior((3,), size, np.random.default_rng(0), np.float32)  # odd ensemble: exercises pair padding
+    ref = ko.transition(x0.astype(np.float64), dt=0.2)
+    out = chain.transition(torch.from_numpy(x0))
+    assert out.device.type == 'cpu' and out.shape == x0.shape  # CPU in -> CPU out, like the reference
+    out = out.numpy()
+    assert np.linalg.norm(out - ref) / np.linalg.norm(ref) < 1e-4
+    assert np.abs(ko.divergence(out.astype(np.float64))).max() < 1e-3
+    # CUDA in -> CUDA out, same numbers
+    out2 = chain.transition(torch.from_numpy(x0).cuda())
+    assert out2.is_cuda and np.array_equal(out2.cpu().numpy(), out)
+
+
+def test_trajectory_and_members_are_independent():
+    from sda_b200.mcs import KolmogorovFlow
+
+    chain = KolmogorovFlow(size=64, dt=0.2)
+    x0 = torch.from_numpy(ko.prior((4,), 64, np.random.default_rng(1), np.float32))
+    traj = chain.trajectory(x0, length=3)
+    assert traj.shape == (3, 4, 2, 64, 64)
+    step = x0
+
+    for i in range(3):
+        step = chain.transition(step)
+        assert torch.equal(step, traj[i])
+
+    assert torch.equal(chain.trajectory(x0, length=3, last=True), traj[-1])
+    # a member's evolution does not depend on its partner in the FFT pair
+    alone = chain.transition(x0[1:2])
+    assert torch.equal(alone[0], traj[0, 1])
+
+
+def test_prior_distribution_and_seeding():
+    from sda_b200.mcs import KolmogorovFlow
+
+    chain = KolmogorovFlow(size=256, dt=0.2)
+    random.seed(3)
+    a = chain.prior((4,))
+    random.seed(3)
+    b = chain.prior((4,))
+    assert torch.equal(a, b) and a.shape == (4, 2, 256, 256)
+    speed = a.square().sum(dim=1).sqrt().amax(dim=(-2, -1))
+    assert torch.allclose(speed, torch.full_like(speed, 3.0), atol=1e-3)  # maximum_velocity=3 (mcs.py:301)
+    assert np.abs(ko.divergence(a.double().numpy())).max() < 1e-3
+    # spectrum peaks near wavenumber 4 (peak_wavenumber=4, mcs.py:302), like the oracle's prior
+    def peak(x):
+        spec = np.abs(np.fft.fft2(x[:, 0].double().numpy())) ** 2
+        k = np.fft.fftfreq(256, 1 / 256)
+        kk = np.sqrt(k[:, None] ** 2 + k[None, :] ** 2).round().astype(int)
+        e = np.bincount(kk.ravel(), weights=spec.mean(0).ravel())[:32]
+        return int(e.argmax())
+
+    ref = torch.from_numpy(ko.prior((4,), 256, np.random.default_rng(0), np.float32))
+    assert abs(peak(a) - peak(ref)) <= 1 and 2 <= peak(a) <= 6
+
+
+def test_observation_kernels(golden):
+    from sda_b200 import _lib
+
+    lib = _lib.load()
+    g = golden('helpers')
+    x = torch.from_numpy(g['x']).cuda()
+    out = torch.empty(3, 2, 4, 4, device='cuda')
+    _lib.check(lib.sdab_coarsen(x.data_ptr(), out.data_ptr(), 6, 16, 16, 4, _lib.stream_ptr()))
+    assert torch.allclose(out.cpu(), torch.from_numpy(g['coarsen4']), atol=1e-6)
+    w = torch.empty(3, 16, 16, device='cuda')
+    _lib.check(lib.sdab_vorticity(x.data_ptr(), w.data_ptr(), 3, 16, 16, _lib.stream_ptr()))
+    assert torch.allclose(w.cpu(), torch.from_numpy(g['vorticity']), atol=1e-6)
