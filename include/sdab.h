@@ -122,7 +122,7 @@ int sdab_conv3x3(const float* x, const float* weight, const float* bias, float* 
 int sdab_conv_profile(int enable);
 int sdab_conv_profile_read(double* ms, double* flops, long long* launches);
 
-/* Number of kernels launched by this library on the calling thread since the last reset. */
+/* Number of kernels launched by this library (all threads) since the last reset. */
 long long sdab_launch_count(int reset);
 
 /* ------------------------------------------------------------------------- *

@@ -1,4 +1,6 @@
 // api.cu -- error reporting, device check and launch accounting of libsdab.
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -7,7 +9,8 @@ namespace sdab {
 
 namespace {
 thread_local std::string g_error;
-thread_local long long g_launches = 0;
+// process-wide: autograd runs backward passes on its own thread
+std::atomic<long long> g_launches{0};
 }  // namespace
 
 void set_error(const std::string& msg) { g_error = msg; }
@@ -28,11 +31,13 @@ struct ConvProfiler {
   double flops = 0.0;
   long long launches = 0;
 };
-thread_local ConvProfiler g_prof;
+ConvProfiler g_prof;
+std::mutex g_prof_mutex;
 }  // namespace
 
 void conv_profile_before(cudaStream_t st) {
   if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   if (g_prof.used + 2 > g_prof.events.size()) {
     for (int i = 0; i < 2; ++i) {
       cudaEvent_t e;
@@ -45,6 +50,7 @@ void conv_profile_before(cudaStream_t st) {
 
 void conv_profile_after(cudaStream_t st, double flops) {
   if (!g_prof.enabled) return;
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   cudaEventRecord(g_prof.events[g_prof.used + 1], st);
   g_prof.used += 2;
   g_prof.flops += flops;
@@ -60,12 +66,11 @@ const char* sdab_last_error(void) { return sdab::g_error.c_str(); }
 int sdab_version(void) { return 100; }
 
 long long sdab_launch_count(int reset) {
-  const long long v = sdab::g_launches;
-  if (reset) sdab::g_launches = 0;
-  return v;
+  return reset ? sdab::g_launches.exchange(0) : sdab::g_launches.load();
 }
 
 int sdab_conv_profile(int enable) {
+  std::lock_guard<std::mutex> lock(sdab::g_prof_mutex);
   sdab::g_prof.enabled = enable != 0;
   sdab::g_prof.used = 0;
   sdab::g_prof.flops = 0.0;
@@ -74,6 +79,7 @@ int sdab_conv_profile(int enable) {
 }
 
 int sdab_conv_profile_read(double* ms, double* flops, long long* launches) {
+  std::lock_guard<std::mutex> lock(sdab::g_prof_mutex);
   double total = 0.0;
   for (size_t i = 0; i + 1 < sdab::g_prof.used; i += 2) {
     if (cudaEventSynchronize(sdab::g_prof.events[i + 1]) != cudaSuccess)

@@ -2,12 +2,15 @@
 //
 // Internal activation formats (DESIGN.md "Data layout in HBM"):
 //   F(C)   fp32, NHWC           [N][H][W][C]
-//   OP(C)  bf16 hi/lo operand   [N][H+2][W+2][2][C]   -- plane 0 = hi, plane 1 = lo,
-//          physically haloed: the ring replicates the opposite edge (circular padding,
-//          nn.Conv2d(padding_mode='circular'), sda/nn.py:125-128) so that every 3x3 tap of
-//          every tile is one in-bounds TMA box.
-//   OP/S2  the same pixels de-interleaved by (row, column) parity:
-//          [N][4][(H+2)/2][(W+2)/2][2][C] -- the input format of the stride-2 heads
+//   OP(C)  bf16 hi/lo operand   [N][2][C/32][H+2][W+2][32] -- plane 0 = hi, plane 1 = lo, then the
+//          32-channel K-block, then the haloed image, channels innermost.  One (plane, K-block) of
+//          128 consecutive pixels is a CONTIGUOUS 8 KB run, so the TMA box that feeds one MMA
+//          K-block streams full cache lines (a pixel-major layout makes every 64 B row a separate
+//          strided request and was measured ~4x slower to fill).  Physically haloed: the ring
+//          replicates the opposite edge (circular padding, nn.Conv2d(padding_mode='circular'),
+//          sda/nn.py:125-128) so that every 3x3 tap of every tile is one in-bounds TMA box.
+//   OP/S2  the same with each image de-interleaved by (row, column) parity:
+//          [N][2][C/32][4][(H+2)/2][(W+2)/2][32] -- the input format of the stride-2 heads
 //          (sda/nn.py:151-159), again so that each tap is one dense TMA box.
 #pragma once
 
@@ -63,18 +66,28 @@ static inline size_t round_up_sz(size_t x, size_t m) { return (x + m - 1) / m * 
 
 // ----------------------------------------------------------------------------- operand layout
 struct OpShape {
-  int N, H, W, C;  // logical image size, channels (multiple of 16)
+  int N, H, W, C;  // logical image size, channels (multiple of 32)
   int s2;          // 1: parity de-interleaved layout
   __host__ __device__ size_t elems() const { return (size_t)N * (H + 2) * (W + 2) * 2 * C; }
   __host__ __device__ size_t bytes() const { return elems() * 2; }
+  // elements between consecutive (plane, K-block) images
+  __host__ __device__ size_t block_stride() const { return (size_t)(H + 2) * (W + 2) * 32; }
+  // element offset from the hi plane to the lo plane of the same K-block
+  __host__ __device__ size_t lo_offset() const { return (size_t)(C / 32) * block_stride(); }
 };
 
-// element offset of the hi plane of padded pixel (hp, wp) of image n; the lo plane is +C
+// element offset of channel 0 of K-block 0 of the hi plane of padded pixel (hp, wp) of image n.
+// Channel c of plane p lives at  + (p * C/32 + c/32) * block_stride() + c % 32.
 __host__ __device__ __forceinline__ size_t op_offset(const OpShape& s, int n, int hp, int wp) {
   const int Hp = s.H + 2, Wp = s.W + 2;
-  if (!s.s2) return (((size_t)n * Hp + hp) * Wp + wp) * 2 * s.C;
-  const int par = (hp & 1) * 2 + (wp & 1);
-  return ((((size_t)n * 4 + par) * (Hp >> 1) + (hp >> 1)) * (Wp >> 1) + (wp >> 1)) * 2 * s.C;
+  size_t pix;
+  if (!s.s2) {
+    pix = (size_t)hp * Wp + wp;
+  } else {
+    const int par = (hp & 1) * 2 + (wp & 1);
+    pix = ((size_t)par * (Hp >> 1) + (hp >> 1)) * (Wp >> 1) + (wp >> 1);
+  }
+  return ((size_t)n * 2 * (s.C / 32) * Hp * Wp + pix) * 32;
 }
 
 // Calls f(hp, wp) for the padded positions that hold logical pixel (h, w): itself plus its
@@ -185,12 +198,13 @@ __device__ __forceinline__ void epilogue_store16(const ConvEpilogue& e, float (&
 #pragma unroll
     for (int j = 0; j < 16; ++j) split_bf16(v[j], hi[j], lo[j]);
     const OpShape s{0, H, W, Cout, 0};
+    const size_t blk = (size_t)(c0 >> 5) * s.block_stride() + (c0 & 31), lo_off = s.lo_offset();
     for_each_replica(h, w, H, W, [&](int hp, int wp) {
-      bf16* dst = e.outOP + op_offset(s, n, hp, wp) + c0;
+      bf16* dst = e.outOP + op_offset(s, n, hp, wp) + blk;
       reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(hi)[0];
       reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(hi)[1];
-      reinterpret_cast<uint4*>(dst + Cout)[0] = reinterpret_cast<const uint4*>(lo)[0];
-      reinterpret_cast<uint4*>(dst + Cout)[1] = reinterpret_cast<const uint4*>(lo)[1];
+      reinterpret_cast<uint4*>(dst + lo_off)[0] = reinterpret_cast<const uint4*>(lo)[0];
+      reinterpret_cast<uint4*>(dst + lo_off)[1] = reinterpret_cast<const uint4*>(lo)[1];
     });
   }
 }

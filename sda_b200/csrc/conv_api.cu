@@ -68,7 +68,11 @@ int sdab_conv3x3(const float* x, const float* weight, const float* bias, float* 
   q.N = N, q.H = H / stride, q.W = W / stride, q.Cin = K, q.Cout = Nn, q.stride = stride, q.mode = mode;
   q.epi.bias = (const float*)(ws + w.bias);
   q.epi.outF = (float*)(ws + w.outf);
-  SDAB_TRY(engine == SDAB_ENGINE_SIMT ? conv3x3_simt(q, st) : conv3x3_umma(q, st));
+  q.flops = 2.0 * 9.0 * (double)N * q.H * q.W * Cin * Cout;
+  conv_profile_before(st);
+  const int status = engine == SDAB_ENGINE_SIMT ? conv3x3_simt(q, st) : conv3x3_umma(q, st);
+  conv_profile_after(st, q.flops);
+  SDAB_TRY(status);
   return unpack_f_to_nchw((const float*)(ws + w.outf), out, N, co, Nn, q.H, q.W, st);
 }
 

@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvProblem p, TileGeom 
       for (int k = 0; k < 32; ++k) {
         float v = 0.f;
         if (valid) {
-          v = __bfloat162float(src[chunk * 32 + k]);
-          if (use_lo) v += __bfloat162float(src[p.Cin + chunk * 32 + k]);
+          const bf16* sk = src + (size_t)chunk * sin.block_stride() + k;
+          v = __bfloat162float(sk[0]);
+          if (use_lo) v += __bfloat162float(sk[sin.lo_offset()]);
         }
         As[t][k] = v;
       }

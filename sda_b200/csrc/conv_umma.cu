@@ -20,6 +20,7 @@
 //                buffered when C_out <= 256 so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -42,6 +43,7 @@ struct UmmaParams {
   int stages, acc_stages;
   int CB, nb;      // N of one MMA, number of N halves
   uint32_t b_plane_bytes, stage_bytes;
+  int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
 
@@ -132,6 +134,28 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
+// One lane of the (converged) warp; the compiler keeps the guarded block on the uniform datapath.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n"
+      "}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
+// hi word of the K-major SWIZZLE_64B descriptor (SBO = 512 B, version 1, layout 4); the lo word is
+// (smem address >> 4) | (LBO = 1) << 16 and is the only part that changes between MMAs.
+constexpr uint32_t kDescHi = (512u >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
+
+// PLANES: 2 = bf16x3 (hi and lo planes, 3 MMAs per product), 1 = bf16.  NB: number of N halves.
+template <int PLANES, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const UmmaParams p) {
@@ -173,78 +197,92 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int kblocks = 9 * p.nchunk;
   const uint32_t acc_stride = p.acc_stages == 2 ? 256u : 0u;
-  const uint32_t b_off = p.planes * kABytes;
+  constexpr uint32_t b_off = PLANES * kABytes;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = p.planes * (kABytes + (uint32_t)p.Cout * 64u);
-      for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x) {
-        int n0, h0, w0;
-        p.g.tile_origin(tile, n0, h0, w0);
-        for (int tap = 0; tap < 9; ++tap) {
-          const int a = tap / 3, b = tap % 3;
-          int cw, ch, cp;
-          if (p.stride == 1) {
-            cw = w0 + b, ch = h0 + a, cp = 0;
-          } else {
-            cw = w0 + (b >> 1), ch = h0 + (a >> 1), cp = (a & 1) * 2 + (b & 1);
-          }
-          for (int chunk = 0; chunk < p.nchunk; ++chunk) {
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+    // The whole warp walks the (warp-uniform) loop; one elected lane issues the copies.
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = PLANES * (kABytes + (uint32_t)p.Cout * 64u);
+    const bool s1 = p.stride == 1;
+    for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x) {
+      int n0, h0, w0;
+      p.g.tile_origin(tile, n0, h0, w0);
+      int brow = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int a = tap / 3, b = tap - 3 * a;
+        const int cw = s1 ? w0 + b : w0 + (b >> 1), ch = s1 ? h0 + a : h0 + (a >> 1);
+        const int cp = s1 ? 0 : (a & 1) * 2 + (b & 1);
+        for (int chunk = 0; chunk < p.nchunk; ++chunk, brow += 2 * p.Cout) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          if (elect_one()) {
             const uint32_t full = bar_full + 8 * stage;
-            mbar_expect_tx(full, tx_bytes);
-            const uint32_t sa = stage0 + stage * p.stage_bytes;
-            const int brow = ((tap * p.nchunk + chunk) * 2) * p.Cout;
-            for (int pl = 0; pl < p.planes; ++pl) {
-              tma_load_5d(sa + pl * kABytes, &tmA, full, chunk * 32 + pl * p.Cin, cw, ch, cp, n0);
-              for (int half = 0; half < p.nb; ++half)
-                tma_load_2d(sa + b_off + pl * p.b_plane_bytes + half * p.CB * 64, &tmB, full, 0,
-                            brow + pl * p.Cout + half * p.CB);
+            if (p.debug & 2) {
+              mbar_arrive(full);
+            } else {
+              mbar_expect_tx(full, tx_bytes);
+              const uint32_t sa = stage0 + stage * p.stage_bytes;
+#pragma unroll
+              for (int pl = 0; pl < PLANES; ++pl) {
+                const int q = pl * p.nchunk + chunk;  // (plane, K-block) image of the operand tensor
+                tma_load_5d(sa + pl * kABytes, &tmA, full, 0, cw, ch, s1 ? q : q * 4 + cp, n0);
+#pragma unroll
+                for (int half = 0; half < NB; ++half)
+                  tma_load_2d(sa + b_off + pl * p.b_plane_bytes + half * p.CB * 64, &tmB, full, 0,
+                              brow + pl * p.Cout + half * p.CB);
+              }
             }
-            if (++stage == p.stages) stage = 0, phase ^= 1;
           }
+          __syncwarp();
+          if (++stage == p.stages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.CB >> 3) << 17) | ((128u >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it % p.acc_stages;
-        const uint32_t acc_phase = (it / p.acc_stages) & 1;
-        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+    // Descriptor lo words are base + compile-time offsets, so a K-block is a straight run of
+    // PLANES == 2 ? 6 : 2 (x NB) tcgen05.mma with no address arithmetic in between.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.CB >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t lo0 = ((stage0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t stage_u = p.stage_bytes >> 4, bplane_u = p.b_plane_bytes >> 4, half_u = (uint32_t)(p.CB * 64) >> 4;
+    const uint32_t CB = (uint32_t)p.CB;
+    const bool no_mma = (p.debug & 1) != 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it % p.acc_stages;
+      const uint32_t acc_phase = (it / p.acc_stages) & 1;
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * acc_stride;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * acc_stride;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(bar_full + 8 * stage, phase);
-          tc_fence_after();
-          const uint32_t sa = stage0 + stage * p.stage_bytes;
-          const uint32_t sb = sa + b_off;
+        if (elect_one()) {
+          const uint32_t a_lo = lo0 + stage * stage_u;
+          const uint32_t b_lo = a_lo + (b_off >> 4);
+          if (!no_mma) {
 #pragma unroll
-          for (int kk = 0; kk < 2; ++kk) {
-            const int npass = p.planes == 2 ? 3 : 1;
-            for (int pass = 0; pass < npass; ++pass) {
-              // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
-              const uint32_t aaddr = sa + (pass == 2 ? kABytes : 0) + kk * 32;
-              const uint32_t baddr = sb + (pass == 1 ? p.b_plane_bytes : 0) + kk * 32;
-              const uint64_t adesc = smem_desc_sw64(aaddr);
-              for (int half = 0; half < p.nb; ++half) {
-                const uint64_t bdesc = smem_desc_sw64(baddr + half * p.CB * 64);
-                umma_bf16(d0 + half * p.CB, adesc, bdesc, idesc, (kb | kk | pass) != 0);
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+              for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
+                // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
+                const uint32_t al = a_lo + (pass == 2 ? (kABytes >> 4) : 0u) + kk * 2;
+                const uint32_t bl = b_lo + (pass == 1 ? bplane_u : 0u) + kk * 2;
+#pragma unroll
+                for (int half = 0; half < NB; ++half)
+                  umma_bf16(d0 + half * CB, desc64(al), desc64(bl + half * half_u), idesc,
+                            (kk | pass) ? 1u : (uint32_t)(kb != 0));
               }
             }
           }
           umma_commit(bar_empty + 8 * stage);
-          if (++stage == p.stages) stage = 0, phase ^= 1;
+          if (kb == kblocks - 1) umma_commit(bar_tfull + 8 * acc);
         }
-        umma_commit(bar_tfull + 8 * acc);
+        __syncwarp();
+        if (++stage == p.stages) stage = 0, phase ^= 1;
       }
     }
   } else {
@@ -264,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
-      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+      for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : p.Cout); c0 += 16) {
         float v[16];
         tmem_ld16(t0 + c0, v);
         if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.H, p.W, p.Cout, c0);
@@ -343,20 +381,25 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
   p.epi = c.epi;
+  {
+    static const int dbg = getenv("SDAB_UMMA_DEBUG") ? atoi(getenv("SDAB_UMMA_DEBUG")) : 0;
+    p.debug = dbg;
+  }
 
-  // A: haloed operand tensor at the input resolution
+  // A: haloed operand tensor at the input resolution, [N][2 * C/32][Hp][Wp][32] (common.cuh)
   const int Hin = c.H * c.stride, Win = c.W * c.stride;
-  const cuuint64_t Hp = Hin + 2, Wp = Win + 2, C2 = 2 * (cuuint64_t)c.Cin;
+  const cuuint64_t Hp = Hin + 2, Wp = Win + 2, Q = 2 * (cuuint64_t)p.nchunk;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5], strides[4];
     if (c.stride == 1) {
-      dims[0] = C2, dims[1] = Wp, dims[2] = Hp, dims[3] = 1, dims[4] = (cuuint64_t)c.N;
-      strides[0] = C2 * 2, strides[1] = Wp * C2 * 2, strides[2] = Hp * Wp * C2 * 2, strides[3] = Hp * Wp * C2 * 2;
+      dims[0] = 32, dims[1] = Wp, dims[2] = Hp, dims[3] = Q, dims[4] = (cuuint64_t)c.N;
+      strides[0] = 64, strides[1] = Wp * 64, strides[2] = Hp * Wp * 64, strides[3] = Q * Hp * Wp * 64;
     } else {
-      dims[0] = C2, dims[1] = Wp / 2, dims[2] = Hp / 2, dims[3] = 4, dims[4] = (cuuint64_t)c.N;
-      strides[0] = C2 * 2, strides[1] = (Wp / 2) * C2 * 2, strides[2] = (Hp / 2) * (Wp / 2) * C2 * 2,
-      strides[3] = 4 * (Hp / 2) * (Wp / 2) * C2 * 2;
+      // parity images: dim 3 indexes (plane, K-block, parity)
+      dims[0] = 32, dims[1] = Wp / 2, dims[2] = Hp / 2, dims[3] = 4 * Q, dims[4] = (cuuint64_t)c.N;
+      strides[0] = 64, strides[1] = (Wp / 2) * 64, strides[2] = (Hp / 2) * (Wp / 2) * 64,
+      strides[3] = Q * Hp * Wp * 64;
     }
     const cuuint32_t box[5] = {32, (cuuint32_t)p.g.BW, (cuuint32_t)p.g.BH, 1, (cuuint32_t)p.g.BN};
     SDAB_TRY(encode(&tmA, c.in, 5, dims, strides, box));
@@ -371,11 +414,21 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   const size_t smem = kCtrlBytes + 1024 + (size_t)p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
-  conv_umma_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  if (p.planes == 2 && p.nb == 1)
+    conv_umma_kernel<2, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  else if (p.planes == 2)
+    conv_umma_kernel<2, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  else if (p.nb == 1)
+    conv_umma_kernel<1, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  else
+    conv_umma_kernel<1, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
   SDAB_LAUNCH_CHECK("conv_umma_kernel");
   return SDAB_OK;
 }

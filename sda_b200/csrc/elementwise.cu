@@ -45,10 +45,11 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, bf16* __restrict__
       for (int c = tx; c < nc; c += 32) {
         bf16 hi, lo;
         split_bf16(tile[c][px], hi, lo);
+        const size_t blk = (size_t)((cb + c) >> 5) * s.block_stride() + ((cb + c) & 31);
         for_each_replica(h, w, H, W, [&](int hp, int wp) {
-          bf16* dst = op + op_offset(s, n, hp, wp);
-          dst[cb + c] = hi;
-          dst[Cpad + cb + c] = lo;
+          bf16* dst = op + op_offset(s, n, hp, wp) + blk;
+          dst[0] = hi;
+          dst[s.lo_offset()] = lo;
         });
       }
     }
@@ -93,10 +94,11 @@ __global__ void f_to_operand_kernel(const float* __restrict__ f, bf16* __restric
   for (int c = lane; c < C; c += 32) {
     bf16 hi, lo;
     split_bf16(src ? src[c] : 0.f, hi, lo);
+    const size_t blk = (size_t)(c >> 5) * s.block_stride() + lane;
     for_each_replica(h, w, H, W, [&](int hp, int wp) {
-      bf16* dst = op + op_offset(s, n, hp, wp);
-      dst[c] = hi;
-      dst[C + c] = lo;
+      bf16* dst = op + op_offset(s, n, hp, wp) + blk;
+      dst[0] = hi;
+      dst[s.lo_offset()] = lo;
     });
   }
 }
@@ -154,9 +156,9 @@ __global__ void ln_forward_kernel(const float* __restrict__ x, const float* __re
         for (int dw = 0; dw < reps; ++dw) {
           const int ho = upsample ? 2 * h + dh : h, wo = upsample ? 2 * w + dw : w;
           for_each_replica(ho, wo, Ho, Wo, [&](int hp, int wp) {
-            bf16* dst = op + op_offset(s, n, hp, wp);
-            dst[c] = hi;
-            dst[C + c] = lo;
+            bf16* dst = op + op_offset(s, n, hp, wp) + (size_t)j * s.block_stride() + lane;
+            dst[0] = hi;
+            dst[s.lo_offset()] = lo;
           });
         }
     }
@@ -194,7 +196,8 @@ __global__ void ln_backward_kernel(const float* __restrict__ ga, const bf16* __r
       } else {
         g[j] = ga[warp * C + c];
       }
-      a[j] = __bfloat162float(ap[c]) + __bfloat162float(ap[C + c]);
+      const bf16* aj = ap + (size_t)j * sa.block_stride() + lane;
+      a[j] = __bfloat162float(aj[0]) + __bfloat162float(aj[sa.lo_offset()]);
       sg += g[j];
       sga += g[j] * a[j];
     }
@@ -214,9 +217,9 @@ __global__ void ln_backward_kernel(const float* __restrict__ ga, const bf16* __r
         bf16 hi, lo;
         split_bf16(v, hi, lo);
         for_each_replica(h, w, H, W, [&](int hp, int wp) {
-          bf16* dst = gxOP + op_offset(so, n, hp, wp);
-          dst[c] = hi;
-          dst[C + c] = lo;
+          bf16* dst = gxOP + op_offset(so, n, hp, wp) + (size_t)j * so.block_stride() + lane;
+          dst[0] = hi;
+          dst[so.lo_offset()] = lo;
         });
       }
     }

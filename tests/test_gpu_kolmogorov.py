@@ -45,9 +45,9 @@ def test_trajectory_and_members_are_independent():
         assert torch.equal(step, traj[i])
 
     assert torch.equal(chain.trajectory(x0, length=3, last=True), traj[-1])
-    # a member's evolution does not depend on its partner in the FFT pair
+    # a member's evolution depends on its partner in the complex-FFT pair only through rounding
     alone = chain.transition(x0[1:2])
-    assert torch.equal(alone[0], traj[0, 1])
+    assert torch.allclose(alone[0], traj[0, 1], rtol=0, atol=2e-5)
 
 
 def test_prior_distribution_and_seeding():
