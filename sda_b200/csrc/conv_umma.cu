@@ -33,6 +33,9 @@ namespace {
 constexpr int kThreads = 192;
 constexpr uint32_t kABytes = 128 * 64;  // one A box: 128 pixels x 32 channels x bf16
 constexpr uint32_t kCtrlBytes = 1024;
+constexpr uint32_t kStageF = 128 * 128;      // epilogue staging: 128 pixels x 32 fp32 channels (SWIZZLE_128B rows)
+constexpr uint32_t kStageO = 128 * 64;       // 128 pixels x 32 bf16 channels (SWIZZLE_64B rows), one per plane
+constexpr uint32_t kStagingBytes = kStageF + 2 * kStageO;
 constexpr uint32_t kSmemBudget = 227 * 1024;
 constexpr int kMaxStages = 8;
 
@@ -43,6 +46,8 @@ struct UmmaParams {
   int stages, acc_stages;
   int CB, nb;      // N of one MMA, number of N halves
   uint32_t b_plane_bytes, stage_bytes;
+  int staged;      // epilogue through shared memory + TMA stores (C_out % 32 == 0)
+  int out_chunks;  // C_out / 32
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
@@ -127,6 +132,78 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// bias / residual / activation / activation-derivative on 32 consecutive channels of one pixel
+// (same order of operations as epilogue_store16).  f receives the value stored to the F output:
+// the pre-activation when e.pre is set, the final value otherwise.
+__device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v)[32], float (&f)[32], size_t off,
+                                                int c0, bool valid) {
+  if (e.bias) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + c0 + j));
+      v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
+    }
+  }
+  if (e.res && valid) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 r = *reinterpret_cast<const float4*>(e.res + off + j);
+      v[j] += r.x, v[j + 1] += r.y, v[j + 2] += r.z, v[j + 3] += r.w;
+    }
+  }
+  if (e.pre) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = v[j];
+  }
+  if (e.act) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], e.act);
+  }
+  if (e.dact && valid) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 c = *reinterpret_cast<const float4*>(e.dact + off + j);
+      v[j] *= act_bwd(c.x, e.dact_kind), v[j + 1] *= act_bwd(c.y, e.dact_kind);
+      v[j + 2] *= act_bwd(c.z, e.dact_kind), v[j + 3] *= act_bwd(c.w, e.dact_kind);
+    }
+  }
+  if (!e.pre) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = v[j];
+  }
+}
+
 // K-major, SWIZZLE_64B shared-memory matrix descriptor: 8-row groups of 64 B rows, 512 B apart.
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
@@ -158,6 +235,7 @@ __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDes
 template <int PLANES, int NB>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmO,
                      const UmmaParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -169,7 +247,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t bar_tfull = base + 128;     // 2 x 8 B
   const uint32_t bar_tempty = base + 144;    // 2 x 8 B
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
-  const uint32_t stage0 = base + kCtrlBytes;
+  const uint32_t staging = base + kCtrlBytes;             // [F 16 KB][hi 8 KB][lo 8 KB]
+  const uint32_t stage0 = staging + kStagingBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -302,15 +381,94 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
-      for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : p.Cout); c0 += 16) {
-        float v[16];
-        tmem_ld16(t0 + c0, v);
-        if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.H, p.W, p.Cout, c0);
+      if (p.debug & 4) {
+        // ablation: no epilogue work
+      } else if (!p.staged) {
+        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          float v[16];
+          tmem_ld16(t0 + c0, v);
+          if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.H, p.W, p.Cout, c0);
+        }
+      } else {
+        // Staged epilogue: every output leaves the SM as full cache lines.  Per 32-channel block the
+        // 128 threads (one pixel each) write their values into swizzled staging tiles; one thread
+        // then issues TMA stores (F: [pixels][C] matrix, OP: the (plane, K-block) image box).
+        const bool issuer = threadIdx.x == 64;  // first epilogue thread
+        const bool wantF = p.epi.outF != nullptr || p.epi.pre != nullptr;
+        const bool wantO = p.epi.outOP != nullptr;
+        const size_t pix0 = ((size_t)n0 * p.H + h0) * p.W + w0;
+        const bool edge = valid && (h == 0 || h == p.H - 1 || w == 0 || w == p.W - 1);
+        for (int cc = 0; cc < p.out_chunks; ++cc) {
+          float v[32], f[32];
+          tmem_ld32(t0 + cc * 32, v);
+          if (cc == p.out_chunks - 1) {
+            // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          }
+          epilogue_math32(p.epi, v, f, pix * p.Cout + cc * 32, cc * 32, valid);
+          // staging tiles free again?  (the previous block's TMA stores have read them)
+          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          epi_barrier();
+          if (wantF) {
+            const uint32_t row = staging + m * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              st_shared_v4(row + ((j ^ (m & 7)) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+          }
+          if (wantO) {
+            __align__(16) bf16 hi[32];
+            __align__(16) bf16 lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) split_bf16(v[j], hi[j], lo[j]);
+            const uint32_t rh = staging + kStageF + m * 64, rl = rh + kStageO;
+            const uint32_t* ph = reinterpret_cast<const uint32_t*>(hi);
+            const uint32_t* pl = reinterpret_cast<const uint32_t*>(lo);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t sw = (j ^ ((m >> 1) & 3)) << 4;
+              st_shared_v4(rh + sw, ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+              st_shared_v4(rl + sw, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+            if (edge) {
+              // halo replicas of edge pixels (the TMA box covers the interior position only)
+              const OpShape so{0, p.H, p.W, p.Cout, 0};
+              const size_t blk = (size_t)cc * so.block_stride(), lo_off = so.lo_offset();
+              bool first = true;
+              for_each_replica(h, w, p.H, p.W, [&](int hp, int wp) {
+                if (first) {
+                  first = false;
+                  return;
+                }
+                bf16* dst = p.epi.outOP + op_offset(so, n, hp, wp) + blk;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                  reinterpret_cast<uint4*>(dst + lo_off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+                }
+              });
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_barrier();
+          if (issuer) {
+            if (wantF) tma_store_2d(&tmF, staging, cc * 32, (int)pix0);
+            if (wantO) {
+              tma_store_5d(&tmO, staging + kStageF, 0, w0 + 1, h0 + 1, cc, n0);
+              tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0 + 1, h0 + 1, p.out_chunks + cc, n0);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        continue;  // tempty already signalled
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
     }
+    if (p.staged && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   __syncwarp();
@@ -337,12 +495,13 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box) {
+           const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_64B) {
   auto fn = get_encode();
   if (!fn) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = fn(map, dtype, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
   return SDAB_OK;
@@ -377,7 +536,10 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   }
   p.b_plane_bytes = (uint32_t)round_up(c.Cout * 64, 1024);
   p.stage_bytes = p.planes * (kABytes + p.b_plane_bytes);
-  p.stages = (int)((kSmemBudget - kCtrlBytes - 1024) / p.stage_bytes);
+  p.staged = c.Cout % 32 == 0;
+  p.out_chunks = c.Cout / 32;
+  SDAB_REQUIRE(!(c.epi.outF && c.epi.pre), "a convolution writes either its output or its pre-activation, not both");
+  p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - kStagingBytes) / p.stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
   p.epi = c.epi;
@@ -411,7 +573,24 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_TRY(encode(&tmB, c.wpk, 2, dims, strides, box));
   }
 
-  const size_t smem = kCtrlBytes + 1024 + (size_t)p.stages * p.stage_bytes;
+  // epilogue outputs (staged path): F as the [pixels][C_out] fp32 matrix, OP as its haloed images
+  CUtensorMap tmF = tmB, tmO = tmB;
+  if (p.staged && (c.epi.outF || c.epi.pre)) {
+    const cuuint64_t dims[2] = {(cuuint64_t)c.Cout, (cuuint64_t)c.N * c.H * c.W};
+    const cuuint64_t strides[1] = {(cuuint64_t)c.Cout * 4};
+    const cuuint32_t box[2] = {32, 128};
+    SDAB_TRY(encode(&tmF, c.epi.outF ? c.epi.outF : c.epi.pre, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                    CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  if (p.staged && c.epi.outOP) {
+    const cuuint64_t Ho = c.H + 2, Wo = c.W + 2, Qo = 2 * (cuuint64_t)p.out_chunks;
+    const cuuint64_t dims[5] = {32, Wo, Ho, Qo, (cuuint64_t)c.N};
+    const cuuint64_t strides[4] = {64, Wo * 64, Ho * Wo * 64, Qo * Ho * Wo * 64};
+    const cuuint32_t box[5] = {32, (cuuint32_t)p.g.BW, (cuuint32_t)p.g.BH, 1, (cuuint32_t)p.g.BN};
+    SDAB_TRY(encode(&tmO, c.epi.outOP, 5, dims, strides, box));
+  }
+
+  const size_t smem = kCtrlBytes + 1024 + kStagingBytes + (size_t)p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -422,13 +601,13 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   }
   const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
   if (p.planes == 2 && p.nb == 1)
-    conv_umma_kernel<2, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    conv_umma_kernel<2, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
   else if (p.planes == 2)
-    conv_umma_kernel<2, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    conv_umma_kernel<2, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
   else if (p.nb == 1)
-    conv_umma_kernel<1, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    conv_umma_kernel<1, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
   else
-    conv_umma_kernel<1, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    conv_umma_kernel<1, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
   SDAB_LAUNCH_CHECK("conv_umma_kernel");
   return SDAB_OK;
 }
