@@ -134,6 +134,17 @@ struct ConvEpilogue {
   bf16* outOP;         // OP(Cout) (normal layout, halo written) or null
   int act;             // forward activation applied to v: 0 none, 1 SiLU, 2 ReLU
   int dact_kind;       // which activation's derivative `dact` refers to (1 SiLU, 2 ReLU)
+  // Channel LayerNorm fused into the epilogue (tcgen05 engine, C_out % 32 == 0 only; the thread that
+  // owns a pixel row of the TMEM accumulator sees all C_out channels):
+  //   ln == 1  forward : outOP = LN_C(f + ln_shift) instead of split(f), f = acc + bias + res (-> outF);
+  //                      this is the operand of the NEXT modulated block (sda/nn.py:27-28,137)
+  //   ln == 2  backward: f = res + (acc - mean_C acc - a * sum_C(acc * a) / (C-1)) * rstd  (-> outF, outOP)
+  int ln;
+  const float* ln_shift;   // forward: [ln_nt][ln_shift_stride] shift of the next block (or null)
+  int ln_shift_stride, ln_nt;
+  float* ln_rstd_out;      // forward: 1 / sqrt(var + eps) per pixel saved here (or null)
+  const bf16* ln_a;        // backward: saved normalised operand OP(C_out) of the block input
+  const float* ln_rstd_in; // backward: saved rstd per pixel
 };
 
 struct ConvProblem {

@@ -204,6 +204,36 @@ __device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v
   }
 }
 
+// 32 consecutive floats / the 32-channel hi+lo value of one pixel with 16 B loads
+__device__ __forceinline__ void load32(const float* __restrict__ src, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = *reinterpret_cast<const float4*>(src + 4 * j);
+    o[4 * j] = t.x, o[4 * j + 1] = t.y, o[4 * j + 2] = t.z, o[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load32_ldg(const float* __restrict__ src, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + 4 * j));
+    o[4 * j] = t.x, o[4 * j + 1] = t.y, o[4 * j + 2] = t.z, o[4 * j + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void load32_hilo(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 a = *reinterpret_cast<const uint4*>(hi + 8 * j);
+    const uint4 b = *reinterpret_cast<const uint4*>(lo + 8 * j);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // bf16 -> fp32 is a 16-bit shift
+      o[8 * j + 2 * k] = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
+      o[8 * j + 2 * k + 1] = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
+    }
+  }
+}
+
 // K-major, SWIZZLE_64B shared-memory matrix descriptor: 8-row groups of 64 B rows, 512 B apart.
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
@@ -398,6 +428,58 @@ __global__ void __launch_bounds__(kThreads, 1)
         const bool wantO = p.epi.outOP != nullptr;
         const size_t pix0 = ((size_t)n0 * p.H + h0) * p.W + w0;
         const bool edge = valid && (h == 0 || h == p.H - 1 || w == 0 || w == p.W - 1);
+        const OpShape so{0, p.H, p.W, p.Cout, 0};
+        const int ln = p.epi.ln;
+        const float invC = 1.f / (float)p.Cout, invC1 = 1.f / (float)(p.Cout - 1);
+        // fused LayerNorm statistics (first pass over the accumulator)
+        float st_a = 0.f, st_b = 0.f, st_r = 1.f;  // forward: mean, -, rstd ; backward: mean(g), sum(g a)/(C-1), rstd
+        const float* shiftp =
+            (ln == 1 && p.epi.ln_shift) ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride
+                                        : nullptr;
+        const bf16* a_pix = (ln == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
+        if (ln == 1) {
+          float s1 = 0.f, s2 = 0.f, K = 0.f;
+          for (int cc = 0; cc < p.out_chunks; ++cc) {
+            float v[32], f[32];
+            tmem_ld32(t0 + cc * 32, v);
+            epilogue_math32(p.epi, v, f, pix * p.Cout + cc * 32, cc * 32, valid);
+            if (shiftp) {
+              float sh[32];
+              load32_ldg(shiftp + cc * 32, sh);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += sh[j];
+            }
+            if (cc == 0) K = f[0];  // shifted one-pass variance: accumulate around the first channel
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float u = f[j] - K;
+              s1 += u;
+              s2 += u * u;
+            }
+          }
+          st_a = K + s1 * invC;
+          const float var = fmaxf(s2 - s1 * s1 * invC, 0.f) * invC1;
+          st_r = 1.f / sqrtf(var + 1e-5f);
+          if (valid && p.epi.ln_rstd_out) p.epi.ln_rstd_out[pix] = st_r;
+        } else if (ln == 2) {
+          float sg = 0.f, sga = 0.f;
+          for (int cc = 0; cc < p.out_chunks; ++cc) {
+            float g[32];
+            tmem_ld32(t0 + cc * 32, g);
+            if (valid) {
+              const bf16* ah = a_pix + (size_t)cc * so.block_stride();
+              float a[32];
+              load32_hilo(ah, ah + so.lo_offset(), a);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                sg += g[j];
+                sga += g[j] * a[j];
+              }
+            }
+          }
+          st_a = sg * invC, st_b = sga * invC1;
+          st_r = valid ? p.epi.ln_rstd_in[pix] : 1.f;
+        }
         for (int cc = 0; cc < p.out_chunks; ++cc) {
           float v[32], f[32];
           tmem_ld32(t0 + cc * 32, v);
@@ -407,7 +489,31 @@ __global__ void __launch_bounds__(kThreads, 1)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
           }
-          epilogue_math32(p.epi, v, f, pix * p.Cout + cc * 32, cc * 32, valid);
+          if (ln == 2) {
+            // backward of the LayerNorm: gx = res + (g - mean g - a sum(g a)/(C-1)) rstd
+            if (valid) {
+              const bf16* ah = a_pix + (size_t)cc * so.block_stride();
+              float a[32];
+              load32_hilo(ah, ah + so.lo_offset(), a);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (v[j] - st_a - a[j] * st_b) * st_r;
+              if (p.epi.res) {
+                load32(p.epi.res + pix * p.Cout + cc * 32, a);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += a[j];
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = v[j];
+          } else {
+            epilogue_math32(p.epi, v, f, pix * p.Cout + cc * 32, cc * 32, valid);
+            if (ln == 1) {
+              float sh[32];
+              if (shiftp) load32_ldg(shiftp + cc * 32, sh);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (f[j] + (shiftp ? sh[j] : 0.f) - st_a) * st_r;
+            }
+          }
           // staging tiles free again?  (the previous block's TMA stores have read them)
           if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           epi_barrier();
@@ -434,7 +540,6 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             if (edge) {
               // halo replicas of edge pixels (the TMA box covers the interior position only)
-              const OpShape so{0, p.H, p.W, p.Cout, 0};
               const size_t blk = (size_t)cc * so.block_stride(), lo_off = so.lo_offset();
               bool first = true;
               for_each_replica(h, w, p.H, p.W, [&](int hp, int wp) {
@@ -539,6 +644,9 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   p.staged = c.Cout % 32 == 0;
   p.out_chunks = c.Cout / 32;
   SDAB_REQUIRE(!(c.epi.outF && c.epi.pre), "a convolution writes either its output or its pre-activation, not both");
+  SDAB_REQUIRE(!c.epi.ln || p.staged, "the fused LayerNorm epilogue needs C_out % 32 == 0");
+  SDAB_REQUIRE(c.epi.ln != 2 || (c.epi.ln_a && c.epi.ln_rstd_in && !c.epi.bias && !c.epi.act && !c.epi.dact),
+               "invalid backward-LayerNorm epilogue");
   p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - kStagingBytes) / p.stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");

@@ -104,65 +104,105 @@ __global__ void f_to_operand_kernel(const float* __restrict__ f, bf16* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// Operand tiles.  The LayerNorm kernels work on a tile of TP consecutive pixels of one image row,
+// staged in shared memory as tile[(q * TP + p) * 32 + c] (q = plane * C/32 + K-block): in the
+// operand tensor one (q, row) run of TP pixels is TP * 64 contiguous bytes, so tiles move with
+// 16 B accesses that are contiguous along the pixel axis.
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnThreads = 256;
+
+// Writes the tile of row h, columns [w0, w0 + TP) into the operand tensor `op` (shape s, normal
+// layout) with its halo replicas.  up != 0: nearest x2 upsample (s is the upsampled shape).
+__device__ __forceinline__ void store_operand_tile(const bf16* tile, bf16* __restrict__ op, const OpShape& s, int n,
+                                                   int h, int w0, int TP, int up, int tid) {
+  const int Hd = s.H, Wd = s.W, Q = 2 * (s.C / 32);
+  int rows[4], nrows = 0;
+  for (int d = (up ? 2 * h : h); d <= (up ? 2 * h + 1 : h); ++d) {
+    rows[nrows++] = d + 1;
+    if (d == 0) rows[nrows++] = Hd + 1;
+    if (d == Hd - 1) rows[nrows++] = 0;
+  }
+  const int DP = up ? 2 * TP : TP, wd0 = up ? 2 * w0 : w0;
+  const bool has_last = wd0 + DP == Wd, has_first = wd0 == 0;
+  const int slots = DP + 2;  // slot DP: left halo (column Wd-1 -> wp 0); slot DP+1: right halo (column 0 -> wp Wd+1)
+  const int total = nrows * Q * slots * 4;
+  const size_t bs = s.block_stride();
+  for (int idx = tid; idx < total; idx += kLnThreads) {
+    const int part = idx & 3;
+    int t = idx >> 2;
+    const int e = t % slots;
+    t /= slots;
+    const int q = t % Q, r = t / Q;
+    int wp, src;
+    if (e < DP) {
+      wp = wd0 + e + 1, src = up ? e >> 1 : e;
+    } else if (e == DP) {
+      if (!has_last) continue;
+      wp = 0, src = TP - 1;
+    } else {
+      if (!has_first) continue;
+      wp = Wd + 1, src = 0;
+    }
+    const uint4 v = *reinterpret_cast<const uint4*>(tile + ((size_t)q * TP + src) * 32 + part * 8);
+    *reinterpret_cast<uint4*>(op + op_offset(s, n, rows[r], wp) + q * bs + part * 8) = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Channel LayerNorm of (x + shift): zuko.nn.LayerNorm(dim=-3) as used at sda/nn.py:137,163 --
 // (u - mean_C u) / sqrt(var_C,unbiased(u) + 1e-5), no affine -- applied to u = x + project(y)
 // (ModResidualBlock.forward, sda/nn.py:27-28).  Output: bf16 hi/lo operand of the next conv,
 // optionally nearest-upsampled x2 (the tails, sda/nn.py:161-170).
+// grid: (W / TP, H, N); one warp per pixel for the statistics (lane <-> channel lane + 32 j).
 // ---------------------------------------------------------------------------------------------
 template <int MAXJ>
-__global__ void ln_forward_kernel(const float* __restrict__ x, const float* __restrict__ shift, int shift_stride,
-                                  int Nt, bf16* __restrict__ op, float* __restrict__ rstd, int N, int H, int W, int C,
-                                  int upsample) {
-  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
-  const size_t total = (size_t)N * H * W;
-  if (warp >= total) return;
-  const int lane = threadIdx.x;
-  const int w = warp % W, h = (warp / W) % H, n = warp / ((size_t)W * H);
-  const float* src = x + warp * C;
+__global__ void __launch_bounds__(kLnThreads)
+    ln_forward_kernel(const float* __restrict__ x, const float* __restrict__ shift, int shift_stride, int Nt,
+                      bf16* __restrict__ op, float* __restrict__ rstd, int N, int H, int W, int C, int upsample,
+                      int TP) {
+  extern __shared__ __align__(16) bf16 ln_tile[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
   const float* sh = shift ? shift + (size_t)(Nt > 1 ? n : 0) * shift_stride : nullptr;
   const int nj = C / 32;
-  float u[MAXJ];
-  float sum = 0.f;
+  for (int p = wid; p < TP; p += kLnThreads / 32) {
+    const size_t pix = ((size_t)n * H + h) * W + w0 + p;
+    const float* src = x + pix * C;
+    float u[MAXJ];
+    float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    if (j < nj) {
-      const int c = lane + 32 * j;
-      u[j] = src[c] + (sh ? __ldg(sh + c) : 0.f);
-      sum += u[j];
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < nj) {
+        const int c = lane + 32 * j;
+        u[j] = src[c] + (sh ? __ldg(sh + c) : 0.f);
+        sum += u[j];
+      }
+    }
+    const float mean = warp_sum(sum) / C;
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < nj) {
+        u[j] -= mean;
+        sq += u[j] * u[j];
+      }
+    }
+    const float var = warp_sum(sq) / (C - 1);
+    const float r = 1.f / sqrtf(var + 1e-5f);
+    if (rstd && lane == 0) rstd[pix] = r;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < nj) {
+        bf16 hi, lo;
+        split_bf16(u[j] * r, hi, lo);
+        ln_tile[((size_t)j * TP + p) * 32 + lane] = hi;
+        ln_tile[((size_t)(nj + j) * TP + p) * 32 + lane] = lo;
+      }
     }
   }
-  const float mean = warp_sum(sum) / C;
-  float sq = 0.f;
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    if (j < nj) {
-      u[j] -= mean;
-      sq += u[j] * u[j];
-    }
-  }
-  const float var = warp_sum(sq) / (C - 1);
-  const float r = 1.f / sqrtf(var + 1e-5f);
-  if (rstd && lane == 0) rstd[warp] = r;
-  const int Ho = upsample ? 2 * H : H, Wo = upsample ? 2 * W : W;
-  const OpShape s{N, Ho, Wo, C, 0};
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    if (j < nj) {
-      const int c = lane + 32 * j;
-      bf16 hi, lo;
-      split_bf16(u[j] * r, hi, lo);
-      const int reps = upsample ? 2 : 1;
-      for (int dh = 0; dh < reps; ++dh)
-        for (int dw = 0; dw < reps; ++dw) {
-          const int ho = upsample ? 2 * h + dh : h, wo = upsample ? 2 * w + dw : w;
-          for_each_replica(ho, wo, Ho, Wo, [&](int hp, int wp) {
-            bf16* dst = op + op_offset(s, n, hp, wp) + (size_t)j * s.block_stride() + lane;
-            dst[0] = hi;
-            dst[s.lo_offset()] = lo;
-          });
-        }
-    }
-  }
+  __syncthreads();
+  const OpShape s{N, upsample ? 2 * H : H, upsample ? 2 * W : W, C, 0};
+  store_operand_tile(ln_tile, op, s, n, h, w0, TP, upsample, threadIdx.x);
 }
 
 // Backward of the channel LayerNorm:
@@ -171,59 +211,70 @@ __global__ void ln_forward_kernel(const float* __restrict__ x, const float* __re
 // the 2x2 block first (adjoint of the nearest upsample of the tails), and the operand holding a is
 // the upsampled one (read at (2h, 2w)).
 template <int MAXJ>
-__global__ void ln_backward_kernel(const float* __restrict__ ga, const bf16* __restrict__ a_op,
-                                   const float* __restrict__ rstd, const float* __restrict__ res,
-                                   float* __restrict__ gxF, bf16* __restrict__ gxOP, int N, int H, int W, int C,
-                                   int pooled) {
-  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
-  const size_t total = (size_t)N * H * W;
-  if (warp >= total) return;
-  const int lane = threadIdx.x;
-  const int w = warp % W, h = (warp / W) % H, n = warp / ((size_t)W * H);
-  const int nj = C / 32;
-  const OpShape sa{N, pooled ? 2 * H : H, pooled ? 2 * W : W, C, 0};
-  const bf16* ap = a_op + op_offset(sa, n, (pooled ? 2 * h : h) + 1, (pooled ? 2 * w : w) + 1);
-  float g[MAXJ], a[MAXJ];
-  float sg = 0.f, sga = 0.f;
-#pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    if (j < nj) {
-      const int c = lane + 32 * j;
-      if (pooled) {
-        const size_t W2 = 2 * (size_t)W;
-        const float* p = ga + (((size_t)n * 2 * H + 2 * h) * W2 + 2 * w) * C + c;
-        g[j] = (p[0] + p[C]) + (p[W2 * C] + p[W2 * C + C]);
-      } else {
-        g[j] = ga[warp * C + c];
-      }
-      const bf16* aj = ap + (size_t)j * sa.block_stride() + lane;
-      a[j] = __bfloat162float(aj[0]) + __bfloat162float(aj[sa.lo_offset()]);
-      sg += g[j];
-      sga += g[j] * a[j];
+__global__ void __launch_bounds__(kLnThreads)
+    ln_backward_kernel(const float* __restrict__ ga, const bf16* __restrict__ a_op, const float* __restrict__ rstd,
+                       const float* __restrict__ res, float* __restrict__ gxF, bf16* __restrict__ gxOP, int N, int H,
+                       int W, int C, int pooled, int TP) {
+  extern __shared__ __align__(16) bf16 ln_tile[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int w0 = blockIdx.x * TP, h = blockIdx.y, n = blockIdx.z;
+  const int nj = C / 32, Q = 2 * nj;
+  // phase 0: the saved normalised activations of the tile -> shared memory
+  {
+    const OpShape sa{N, pooled ? 2 * H : H, pooled ? 2 * W : W, C, 0};
+    const size_t bs = sa.block_stride();
+    const int hp = (pooled ? 2 * h : h) + 1;
+    for (int idx = threadIdx.x; idx < Q * TP * 4; idx += kLnThreads) {
+      const int part = idx & 3, p = (idx >> 2) % TP, q = (idx >> 2) / TP;
+      const int wp = (pooled ? 2 * (w0 + p) : w0 + p) + 1;
+      *reinterpret_cast<uint4*>(ln_tile + ((size_t)q * TP + p) * 32 + part * 8) =
+          *reinterpret_cast<const uint4*>(a_op + op_offset(sa, n, hp, wp) + q * bs + part * 8);
     }
   }
-  sg = warp_sum(sg) / C;
-  sga = warp_sum(sga) / (C - 1);
-  const float r = rstd[warp];
-  const OpShape so{N, H, W, C, 0};
+  __syncthreads();
+  for (int p = wid; p < TP; p += kLnThreads / 32) {
+    const int w = w0 + p;
+    const size_t pix = ((size_t)n * H + h) * W + w;
+    float g[MAXJ], a[MAXJ];
+    float sg = 0.f, sga = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXJ; ++j) {
-    if (j < nj) {
-      const int c = lane + 32 * j;
-      float v = (g[j] - sg - a[j] * sga) * r;
-      if (res) v += res[warp * C + c];
-      if (gxF) gxF[warp * C + c] = v;
-      if (gxOP) {
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < nj) {
+        const int c = lane + 32 * j;
+        if (pooled) {
+          const size_t W2 = 2 * (size_t)W;
+          const float* q = ga + (((size_t)n * 2 * H + 2 * h) * W2 + 2 * w) * C + c;
+          g[j] = (q[0] + q[C]) + (q[W2 * C] + q[W2 * C + C]);
+        } else {
+          g[j] = ga[pix * C + c];
+        }
+        a[j] = __bfloat162float(ln_tile[((size_t)j * TP + p) * 32 + lane]) +
+               __bfloat162float(ln_tile[((size_t)(nj + j) * TP + p) * 32 + lane]);
+        sg += g[j];
+        sga += g[j] * a[j];
+      }
+    }
+    sg = warp_sum(sg) / C;
+    sga = warp_sum(sga) / (C - 1);
+    const float r = rstd[pix];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < nj) {
+        const int c = lane + 32 * j;
+        float v = (g[j] - sg - a[j] * sga) * r;
+        if (res) v += res[pix * C + c];
+        if (gxF) gxF[pix * C + c] = v;
         bf16 hi, lo;
         split_bf16(v, hi, lo);
-        for_each_replica(h, w, H, W, [&](int hp, int wp) {
-          bf16* dst = gxOP + op_offset(so, n, hp, wp) + (size_t)j * so.block_stride() + lane;
-          dst[0] = hi;
-          dst[so.lo_offset()] = lo;
-        });
+        ln_tile[((size_t)j * TP + p) * 32 + lane] = hi;
+        ln_tile[((size_t)(nj + j) * TP + p) * 32 + lane] = lo;
       }
     }
   }
+  if (!gxOP) return;
+  __syncthreads();
+  const OpShape so{N, H, W, C, 0};
+  store_operand_tile(ln_tile, gxOP, so, n, h, w0, TP, 0, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,13 +362,16 @@ int f_to_operand(const float* f, bf16* op, int N, int H, int W, int C, int kind,
 int ln_forward(const float* x, const float* shift, int shift_stride, int Nt, bf16* op, float* rstd, int N, int H, int W,
                int C, int upsample, cudaStream_t st) {
   SDAB_REQUIRE(C % 32 == 0 && C <= 512, "LayerNorm channels must be a multiple of 32, at most 512");
-  const dim3 grid = warp_grid((size_t)N * H * W), block(32, kWarpsPerBlock);
+  const int TP = W < 32 ? W : (C > 384 ? 16 : 32);
+  SDAB_REQUIRE(W % TP == 0, "image width must be a multiple of the LayerNorm tile");
+  const dim3 grid(W / TP, H, N);
+  const size_t smem = (size_t)4 * C * TP;
   if (C <= 128)
-    ln_forward_kernel<4><<<grid, block, 0, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample);
+    ln_forward_kernel<4><<<grid, kLnThreads, smem, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample, TP);
   else if (C <= 256)
-    ln_forward_kernel<8><<<grid, block, 0, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample);
+    ln_forward_kernel<8><<<grid, kLnThreads, smem, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample, TP);
   else
-    ln_forward_kernel<16><<<grid, block, 0, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample);
+    ln_forward_kernel<16><<<grid, kLnThreads, smem, st>>>(x, shift, shift_stride, Nt, op, rstd, N, H, W, C, upsample, TP);
   SDAB_LAUNCH_CHECK("ln_forward_kernel");
   return SDAB_OK;
 }
@@ -325,13 +379,16 @@ int ln_forward(const float* x, const float* shift, int shift_stride, int Nt, bf1
 int ln_backward(const float* ga, const bf16* a_op, const float* rstd, const float* res, float* gxF, bf16* gxOP, int N,
                 int H, int W, int C, int pooled, cudaStream_t st) {
   SDAB_REQUIRE(C % 32 == 0 && C <= 512, "LayerNorm channels must be a multiple of 32, at most 512");
-  const dim3 grid = warp_grid((size_t)N * H * W), block(32, kWarpsPerBlock);
+  const int TP = W < 32 ? W : (C > 384 ? 16 : 32);
+  SDAB_REQUIRE(W % TP == 0, "image width must be a multiple of the LayerNorm tile");
+  const dim3 grid(W / TP, H, N);
+  const size_t smem = (size_t)4 * C * TP;
   if (C <= 128)
-    ln_backward_kernel<4><<<grid, block, 0, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled);
+    ln_backward_kernel<4><<<grid, kLnThreads, smem, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled, TP);
   else if (C <= 256)
-    ln_backward_kernel<8><<<grid, block, 0, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled);
+    ln_backward_kernel<8><<<grid, kLnThreads, smem, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled, TP);
   else
-    ln_backward_kernel<16><<<grid, block, 0, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled);
+    ln_backward_kernel<16><<<grid, kLnThreads, smem, st>>>(ga, a_op, rstd, res, gxF, gxOP, N, H, W, C, pooled, TP);
   SDAB_LAUNCH_CHECK("ln_backward_kernel");
   return SDAB_OK;
 }

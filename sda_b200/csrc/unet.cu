@@ -300,12 +300,39 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
   SDAB_TRY(time_shifts(y, (const float*)(pk + h->off_projw), (const float*)(pk + h->off_projb), F(p.shift), Nt,
                        h->shift_rows, h->d.mod_features, st));
 
-  // one modulated residual block: cur -> dst (F), optionally also the raw operand of dst
-  auto block = [&](int d, int j, int c1, const float* cur, float* dst, bf16* dst_op) -> int {
+  // With the tcgen05 engine the channel LayerNorm of the NEXT block is fused into the epilogue of the
+  // convolution that produces the residual stream (ConvEpilogue::ln == 1): `prenorm` is the block
+  // whose operand has already been produced that way.
+  const bool fuse = engine == SDAB_ENGINE_UMMA;
+  int prenorm = -1;
+  auto level_of = [&](int j) {  // level of block j
+    for (int d = 0; d < D; ++d) {
+      for (int v : h->desc_blk[d])
+        if (v == j) return d;
+      for (int v : h->asc_blk[d])
+        if (v == j) return d;
+    }
+    return -1;
+  };
+  auto fuse_ln = [&](ConvProblem& q, int next_j) {
+    if (!fuse || next_j < 0) return;
+    const int d = level_of(next_j);
+    q.epi.ln = 1;
+    q.epi.ln_shift = F(p.shift) + h->block_shift_off[next_j];
+    q.epi.ln_shift_stride = h->shift_rows, q.epi.ln_nt = Nt;
+    q.epi.ln_rstd_out = save ? F(p.rstd[next_j]) : nullptr;
+    q.epi.outOP = save ? OP(p.aop[next_j]) : OP(p.aop_tmp[d]);
+    prenorm = next_j;
+  };
+
+  // one modulated residual block: cur -> dst (F); dst_op: also the raw operand of dst; next_j: the
+  // block that consumes dst (its LayerNorm is fused into conv2), or -1
+  auto block = [&](int d, int j, int c1, const float* cur, float* dst, bf16* dst_op, int next_j) -> int {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
     bf16* aop = save ? OP(p.aop[j]) : OP(p.aop_tmp[d]);
-    SDAB_TRY(ln_forward(cur, F(p.shift) + h->block_shift_off[j], h->shift_rows, Nt, aop,
-                        save ? F(p.rstd[j]) : nullptr, N, Hd, Wd, C, 0, st));
+    if (prenorm != j)
+      SDAB_TRY(ln_forward(cur, F(p.shift) + h->block_shift_off[j], h->shift_rows, Nt, aop,
+                          save ? F(p.rstd[j]) : nullptr, N, Hd, Wd, C, 0, st));
     ConvProblem q{};
     q.in = aop, q.wpk = wf(c1), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = C, q.stride = 1, q.mode = mode;
     q.epi.bias = bias(c1), q.epi.pre = save ? F(p.c1[j]) : nullptr, q.epi.act = act, q.epi.outOP = OP(p.hop[d]);
@@ -314,6 +341,7 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
     r.in = OP(p.hop[d]), r.wpk = wf(c1 + 1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
     r.mode = mode;
     r.epi.bias = bias(c1 + 1), r.epi.res = cur, r.epi.outF = dst, r.epi.outOP = dst_op;
+    if (!dst_op) fuse_ln(r, next_j);
     return run_conv(engine, r, st);
   };
 
@@ -328,12 +356,14 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = h->convs[ci].kf, q.Cout = C, q.stride = d == 0 ? 1 : 2;
       q.mode = mode, q.epi.bias = bias(ci);
       q.epi.outF = nb == 0 ? F(p.skip[d]) : F(p.x0[d]);
+      fuse_ln(q, nb > 0 ? h->desc_blk[d][0] : -1);
       SDAB_TRY(run_conv(engine, q, st, h->convs[ci].cin));
       cur = q.epi.outF;
     }
     for (int b = 0; b < nb; ++b) {
       float* dst = b == nb - 1 ? F(p.skip[d]) : (cur == F(p.x0[d]) ? F(p.x1[d]) : F(p.x0[d]));
-      SDAB_TRY(block(d, h->desc_blk[d][b], h->desc_c1[d][b], cur, dst, nullptr));
+      const int next_j = b + 1 < nb ? h->desc_blk[d][b + 1] : (d == D - 1 ? h->asc_blk[d][0] : -1);
+      SDAB_TRY(block(d, h->desc_blk[d][b], h->desc_c1[d][b], cur, dst, nullptr, next_j));
       cur = dst;
     }
     if (d < D - 1) SDAB_TRY(f_to_operand(cur, OP(p.xs2[d]), N, Hd, Wd, C, 1, st));
@@ -345,7 +375,8 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
     for (int b = 0; b < nb; ++b) {
       float* dst = cur == F(p.x0[d]) ? F(p.x1[d]) : F(p.x0[d]);
       const bool fin = d == 0 && b == nb - 1;
-      SDAB_TRY(block(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst, fin ? OP(p.finop) : nullptr));
+      const int next_j = b + 1 < nb ? h->asc_blk[d][b + 1] : -1;
+      SDAB_TRY(block(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst, fin ? OP(p.finop) : nullptr, next_j));
       have_finop = have_finop || fin;
       cur = dst;
     }
@@ -356,6 +387,7 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       q.in = OP(p.upop[d]), q.wpk = wf(ci), q.N = N, q.H = 2 * Hd, q.W = 2 * Wd, q.Cin = C;
       q.Cout = h->d.hidden_channels[d - 1], q.stride = 1, q.mode = mode;
       q.epi.bias = bias(ci), q.epi.res = F(p.skip[d - 1]), q.epi.outF = F(p.x0[d - 1]);
+      fuse_ln(q, h->d.hidden_blocks[d - 1] > 0 ? h->asc_blk[d - 1][0] : -1);
       SDAB_TRY(run_conv(engine, q, st));
       cur = q.epi.outF;
     } else {
@@ -409,6 +441,12 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
     ConvProblem r{};
     r.in = OP(p.gc1op[d]), r.wpk = wb(c1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
     r.mode = mode;
+    if (engine == SDAB_ENGINE_UMMA) {
+      // LayerNorm adjoint + residual fused into the epilogue of conv1^T (ConvEpilogue::ln == 2)
+      r.epi.ln = 2, r.epi.ln_a = OP(p.aop[j]), r.epi.ln_rstd_in = F(p.rstd[j]);
+      r.epi.res = cur, r.epi.outF = dst, r.epi.outOP = GOP(d);
+      return run_conv(engine, r, st);
+    }
     r.epi.outF = GA(d);
     SDAB_TRY(run_conv(engine, r, st));
     return ln_backward(GA(d), OP(p.aop[j]), F(p.rstd[j]), cur, dst, GOP(d), N, Hd, Wd, C, 0, st);
