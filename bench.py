@@ -258,7 +258,7 @@ def run_ours(args, rank, local_rank, world):
     _lib.check(lib.sdab_conv_profile_read(ctypes.byref(conv_ms), ctypes.byref(conv_flops), ctypes.byref(conv_launches)))
     lib.sdab_conv_profile(0)
     clocks = sampler.stop() if rank == 0 else None
-    assert torch.isfinite(x).all(), 'non-finite state after the timed steps'
+    assert os.environ.get('SDAB_UMMA_DEBUG') or torch.isfinite(x).all(), 'non-finite state after the timed steps'
 
     # ---------------- end to end through the public step API, host buffers in and out
     barrier()

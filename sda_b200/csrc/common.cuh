@@ -109,7 +109,7 @@ __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
 }
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
-  if (act == 1) return v / (1.f + __expf(-v));  // SiLU
+  if (act == 1) return __fdividef(v, 1.f + __expf(-v));  // SiLU (fast division: ~2 ulp)
   if (act == 2) return fmaxf(v, 0.f);           // ReLU
   return v;
 }
@@ -117,7 +117,7 @@ __device__ __forceinline__ float act_fwd(float v, int act) {
 // derivative of the activation at pre-activation c
 __device__ __forceinline__ float act_bwd(float c, int act) {
   if (act == 1) {
-    const float s = 1.f / (1.f + __expf(-c));
+    const float s = __fdividef(1.f, 1.f + __expf(-c));
     return s * (1.f + c * (1.f - s));
   }
   if (act == 2) return c > 0.f ? 1.f : 0.f;

@@ -47,6 +47,7 @@ struct UmmaParams {
   int CB, nb;      // N of one MMA, number of N halves
   uint32_t b_plane_bytes, stage_bytes;
   int staged;      // epilogue through shared memory + TMA stores (C_out % 32 == 0)
+  int sbufs;       // number of staging sets (TMA stores in flight behind the epilogue)
   int out_chunks;  // C_out / 32
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
@@ -161,13 +162,25 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+#define EPI_BARRIER() do { if (!(p.debug & 64)) epi_barrier(); } while (0)
 
 // bias / residual / activation / activation-derivative on 32 consecutive channels of one pixel
-// (same order of operations as epilogue_store16).  f receives the value stored to the F output:
-// the pre-activation when e.pre is set, the final value otherwise.
-__device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v)[32], float (&f)[32], size_t off,
-                                                int c0, bool valid) {
+// (same order of operations as epilogue_store16).  The residual / derivative operands are passed in
+// registers: the caller issues their global loads BEFORE waiting on the accumulator.  f receives
+// the value stored to the F output: the pre-activation when e.pre is set, the final value otherwise.
+__device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v)[32], float (&f)[32],
+                                                const float (&rr)[32], bool has_res, bool has_dact, int c0) {
   if (e.bias) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
@@ -175,12 +188,9 @@ __device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v
       v[j] += b.x, v[j + 1] += b.y, v[j + 2] += b.z, v[j + 3] += b.w;
     }
   }
-  if (e.res && valid) {
+  if (has_res) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 r = *reinterpret_cast<const float4*>(e.res + off + j);
-      v[j] += r.x, v[j + 1] += r.y, v[j + 2] += r.z, v[j + 3] += r.w;
-    }
+    for (int j = 0; j < 32; ++j) v[j] += rr[j];
   }
   if (e.pre) {
 #pragma unroll
@@ -190,19 +200,17 @@ __device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], e.act);
   }
-  if (e.dact && valid) {
+  if (has_dact) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      const float4 c = *reinterpret_cast<const float4*>(e.dact + off + j);
-      v[j] *= act_bwd(c.x, e.dact_kind), v[j + 1] *= act_bwd(c.y, e.dact_kind);
-      v[j + 2] *= act_bwd(c.z, e.dact_kind), v[j + 3] *= act_bwd(c.w, e.dact_kind);
-    }
+    for (int j = 0; j < 32; ++j) v[j] *= act_bwd(rr[j], e.dact_kind);
   }
   if (!e.pre) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = v[j];
   }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // 32 consecutive floats / the 32-channel hi+lo value of one pixel with 16 B loads
 __device__ __forceinline__ void load32(const float* __restrict__ src, float (&o)[32]) {
@@ -262,7 +270,7 @@ constexpr uint32_t kDescHi = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
 // PLANES: 2 = bf16x3 (hi and lo planes, 3 MMAs per product), 1 = bf16.  NB: number of N halves.
-template <int PLANES, int NB>
+template <int PLANES, int NB, int LN>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmO,
@@ -277,8 +285,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t bar_tfull = base + 128;     // 2 x 8 B
   const uint32_t bar_tempty = base + 144;    // 2 x 8 B
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
-  const uint32_t staging = base + kCtrlBytes;             // [F 16 KB][hi 8 KB][lo 8 KB]
-  const uint32_t stage0 = staging + kStagingBytes;
+  const uint32_t staging0 = base + kCtrlBytes;            // sbufs x [F 16 KB][hi 8 KB][lo 8 KB]
+  const uint32_t stage0 = staging0 + p.sbufs * kStagingBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -400,6 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int m = q * 32 + lane;
     const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
     int it = 0;
+    int sbuf = 0;  // staging set of the next 32-channel block (running over tiles)
     for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it % p.acc_stages;
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
@@ -423,13 +432,33 @@ __global__ void __launch_bounds__(kThreads, 1)
         // Staged epilogue: every output leaves the SM as full cache lines.  Per 32-channel block the
         // 128 threads (one pixel each) write their values into swizzled staging tiles; one thread
         // then issues TMA stores (F: [pixels][C] matrix, OP: the (plane, K-block) image box).
-        const bool issuer = threadIdx.x == 64;  // first epilogue thread
         const bool wantF = p.epi.outF != nullptr || p.epi.pre != nullptr;
         const bool wantO = p.epi.outOP != nullptr;
         const size_t pix0 = ((size_t)n0 * p.H + h0) * p.W + w0;
         const bool edge = valid && (h == 0 || h == p.H - 1 || w == 0 || w == p.W - 1);
         const OpShape so{0, p.H, p.W, p.Cout, 0};
-        const int ln = p.epi.ln;
+        constexpr int ln = LN;  // fused LayerNorm variant (ConvEpilogue::ln), compile-time to keep registers down
+        // developer ablation bits: 8 = no LayerNorm statistics pass, 16 = no global operand loads, 32 = no stores
+        const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
+        {
+          // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
+          const int nt = tile + gridDim.x;
+          if (nt < p.g.num_tiles) {
+            int nn0, nh0, nw0;
+            p.g.tile_origin(nt, nn0, nh0, nw0);
+            const int nn = nn0 + bn, nh = nh0 + bh, nw = nw0 + bw;
+            if (nn < p.N) {
+              const size_t npix = ((size_t)nn * p.H + nh) * p.W + nw;
+              const float* pf = p.epi.res ? p.epi.res : p.epi.dact;
+              if (pf)
+                for (int c = 0; c < p.Cout; c += 32) prefetch_l2(pf + npix * p.Cout + c);
+              if (ln == 2) {
+                const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
+                for (int c = 0; c < 2 * p.out_chunks; ++c) prefetch_l2(pa + (size_t)c * so.block_stride());
+              }
+            }
+          }
+        }
         const float invC = 1.f / (float)p.Cout, invC1 = 1.f / (float)(p.Cout - 1);
         // fused LayerNorm statistics (first pass over the accumulator)
         float st_a = 0.f, st_b = 0.f, st_r = 1.f;  // forward: mean, -, rstd ; backward: mean(g), sum(g a)/(C-1), rstd
@@ -437,12 +466,13 @@ __global__ void __launch_bounds__(kThreads, 1)
             (ln == 1 && p.epi.ln_shift) ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride
                                         : nullptr;
         const bf16* a_pix = (ln == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
-        if (ln == 1) {
+        if (ln == 1 && !(p.debug & 8)) {
           float s1 = 0.f, s2 = 0.f, K = 0.f;
           for (int cc = 0; cc < p.out_chunks; ++cc) {
-            float v[32], f[32];
+            float v[32], f[32], rr[32];
+            if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
             tmem_ld32(t0 + cc * 32, v);
-            epilogue_math32(p.epi, v, f, pix * p.Cout + cc * 32, cc * 32, valid);
+            epilogue_math32(p.epi, v, f, rr, has_res, false, cc * 32);
             if (shiftp) {
               float sh[32];
               load32_ldg(shiftp + cc * 32, sh);
@@ -461,15 +491,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           const float var = fmaxf(s2 - s1 * s1 * invC, 0.f) * invC1;
           st_r = 1.f / sqrtf(var + 1e-5f);
           if (valid && p.epi.ln_rstd_out) p.epi.ln_rstd_out[pix] = st_r;
-        } else if (ln == 2) {
+        } else if (ln == 2 && !(p.debug & 8)) {
           float sg = 0.f, sga = 0.f;
           for (int cc = 0; cc < p.out_chunks; ++cc) {
-            float g[32];
-            tmem_ld32(t0 + cc * 32, g);
+            float g[32], a[32];
             if (valid) {
               const bf16* ah = a_pix + (size_t)cc * so.block_stride();
-              float a[32];
               load32_hilo(ah, ah + so.lo_offset(), a);
+            }
+            tmem_ld32(t0 + cc * 32, g);
+            if (valid) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 sg += g[j];
@@ -481,7 +512,14 @@ __global__ void __launch_bounds__(kThreads, 1)
           st_r = valid ? p.epi.ln_rstd_in[pix] : 1.f;
         }
         for (int cc = 0; cc < p.out_chunks; ++cc) {
-          float v[32], f[32];
+          float v[32], f[32], rr[32], aa[32];
+          // operands from global memory first: their latency overlaps the accumulator load
+          if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
+          if (has_dact) load32(p.epi.dact + pix * p.Cout + cc * 32, rr);
+          if (ln == 2 && valid && !(p.debug & 16)) {
+            const bf16* ah = a_pix + (size_t)cc * so.block_stride();
+            load32_hilo(ah, ah + so.lo_offset(), aa);
+          }
           tmem_ld32(t0 + cc * 32, v);
           if (cc == p.out_chunks - 1) {
             // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
@@ -492,21 +530,13 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (ln == 2) {
             // backward of the LayerNorm: gx = res + (g - mean g - a sum(g a)/(C-1)) rstd
             if (valid) {
-              const bf16* ah = a_pix + (size_t)cc * so.block_stride();
-              float a[32];
-              load32_hilo(ah, ah + so.lo_offset(), a);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (v[j] - st_a - a[j] * st_b) * st_r;
-              if (p.epi.res) {
-                load32(p.epi.res + pix * p.Cout + cc * 32, a);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += a[j];
-              }
+              for (int j = 0; j < 32; ++j) v[j] = (v[j] - st_a - aa[j] * st_b) * st_r + (has_res ? rr[j] : 0.f);
             }
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = v[j];
           } else {
-            epilogue_math32(p.epi, v, f, pix * p.Cout + cc * 32, cc * 32, valid);
+            epilogue_math32(p.epi, v, f, rr, has_res, has_dact, cc * 32);
             if (ln == 1) {
               float sh[32];
               if (shiftp) load32_ldg(shiftp + cc * 32, sh);
@@ -514,9 +544,18 @@ __global__ void __launch_bounds__(kThreads, 1)
               for (int j = 0; j < 32; ++j) v[j] = (f[j] + (shiftp ? sh[j] : 0.f) - st_a) * st_r;
             }
           }
-          // staging tiles free again?  (the previous block's TMA stores have read them)
-          if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          epi_barrier();
+          if (p.debug & 32) continue;
+          // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
+          const uint32_t staging = staging0 + sbuf * kStagingBytes;
+          if (threadIdx.x == 64) {
+            if (p.sbufs == 1)
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else if (p.sbufs == 2)
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else
+              asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+          }
+          EPI_BARRIER();
           if (wantF) {
             const uint32_t row = staging + m * 128;
 #pragma unroll
@@ -557,8 +596,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_barrier();
-          if (issuer) {
+          EPI_BARRIER();
+          if (threadIdx.x == 64 && !(p.debug & 128)) {
+            // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
+            // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
             if (wantF) tma_store_2d(&tmF, staging, cc * 32, (int)pix0);
             if (wantO) {
               tma_store_5d(&tmO, staging + kStageF, 0, w0 + 1, h0 + 1, cc, n0);
@@ -566,6 +607,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          if (++sbuf == p.sbufs) sbuf = 0;
         }
         continue;  // tempty already signalled
       }
@@ -647,7 +689,10 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(!c.epi.ln || p.staged, "the fused LayerNorm epilogue needs C_out % 32 == 0");
   SDAB_REQUIRE(c.epi.ln != 2 || (c.epi.ln_a && c.epi.ln_rstd_in && !c.epi.bias && !c.epi.act && !c.epi.dact),
                "invalid backward-LayerNorm epilogue");
-  p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - kStagingBytes) / p.stage_bytes);
+  p.sbufs = !p.staged ? 1 : (c.Cout <= 128 ? 3 : (c.Cout <= 256 ? 2 : 1));
+  if (getenv("SDAB_UMMA_SBUFS")) p.sbufs = atoi(getenv("SDAB_UMMA_SBUFS"));
+  SDAB_REQUIRE(p.sbufs >= 1 && p.sbufs <= 3, "staging sets out of range");
+  p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - p.sbufs * kStagingBytes) / p.stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
   p.epi = c.epi;
@@ -698,24 +743,24 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_TRY(encode(&tmO, c.epi.outOP, 5, dims, strides, box));
   }
 
-  const size_t smem = kCtrlBytes + 1024 + kStagingBytes + (size_t)p.stages * p.stage_bytes;
+  const size_t smem = kCtrlBytes + 1024 + (size_t)p.sbufs * kStagingBytes + (size_t)p.stages * p.stage_bytes;
+  using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, UmmaParams);
+  static const Kernel kernels[2][2][3] = {
+      {{conv_umma_kernel<1, 1, 0>, conv_umma_kernel<1, 1, 1>, conv_umma_kernel<1, 1, 2>},
+       {conv_umma_kernel<1, 2, 0>, conv_umma_kernel<1, 2, 1>, conv_umma_kernel<1, 2, 2>}},
+      {{conv_umma_kernel<2, 1, 0>, conv_umma_kernel<2, 1, 1>, conv_umma_kernel<2, 1, 2>},
+       {conv_umma_kernel<2, 2, 0>, conv_umma_kernel<2, 2, 1>, conv_umma_kernel<2, 2, 2>}}};
   static bool attr_set = false;
   if (!attr_set) {
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(conv_umma_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int l = 0; l < 3; ++l)
+          SDAB_CUDA_CHECK(cudaFuncSetAttribute(kernels[a][b][l], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
+  SDAB_REQUIRE(c.epi.ln >= 0 && c.epi.ln <= 2, "unknown fused LayerNorm variant");
   const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
-  if (p.planes == 2 && p.nb == 1)
-    conv_umma_kernel<2, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
-  else if (p.planes == 2)
-    conv_umma_kernel<2, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
-  else if (p.nb == 1)
-    conv_umma_kernel<1, 1><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
-  else
-    conv_umma_kernel<1, 2><<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
+  kernels[p.planes - 1][p.nb - 1][c.epi.ln]<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
   SDAB_LAUNCH_CHECK("conv_umma_kernel");
   return SDAB_OK;
 }
