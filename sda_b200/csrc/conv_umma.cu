@@ -102,6 +102,51 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "memory");
 }
 
+// 2-CTA (cta_group::2) variants: the copy lands in the executing CTA's shared memory but completes
+// its bytes on the LEADER CTA's barrier (peer bit of the shared::cluster address cleared).
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, "
+      "%5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & kPeerMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in BOTH CTAs of the pair once the MMAs issued so far finish
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+// arrive on the leader CTA's barrier (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerMask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -270,7 +315,10 @@ constexpr uint32_t kDescHi = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
 // PLANES: 2 = bf16x3 (hi and lo planes, 3 MMAs per product), 1 = bf16.  NB: number of N halves.
-template <int PLANES, int NB, int LN>
+// CTA2: the two CTAs of a cluster pair compute two adjacent M tiles with ONE tcgen05.mma.cta_group::2
+// (M = 256): each CTA stages its own A tile and only HALF of the B rows, which halves the weight
+// traffic and the shared-memory reads per MMA -- the kernel is shared-memory-bandwidth bound otherwise.
+template <int PLANES, int NB, int LN, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1)
     conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmO,
@@ -289,6 +337,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t stage0 = staging0 + p.sbufs * kStagingBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank = 0;
+  if constexpr (CTA2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = rank == 0;
+  // tile walk: CTA2 pairs take tiles (2 c, 2 c + 1); a pair whose second tile is past the end still
+  // runs it as a ghost (out-of-range TMA boxes read zeros, the epilogue masks it)
+  const int tile_begin = CTA2 ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
+  const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -297,18 +352,25 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, CTA2 ? 8 : 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 160), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 160), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 160), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();  // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -321,9 +383,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     // The whole warp walks the (warp-uniform) loop; one elected lane issues the copies.
     int stage = 0;
     uint32_t phase = 0;
-    const uint32_t tx_bytes = PLANES * (kABytes + (uint32_t)p.Cout * 64u);
+    // bytes landing per K-block: this CTA's A planes and B rows; in CTA2 mode the leader's barrier
+    // also receives the peer's bytes
+    const int cbh = CTA2 ? p.CB / 2 : p.CB;  // B rows of one N half held by this CTA
+    const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * PLANES * (kABytes + (uint32_t)(NB * cbh) * 64u);
     const bool s1 = p.stride == 1;
-    for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x) {
+    for (int tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       int n0, h0, w0;
       p.g.tile_origin(tile, n0, h0, w0);
       int brow = 0;
@@ -336,18 +401,26 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (elect_one()) {
             const uint32_t full = bar_full + 8 * stage;
             if (p.debug & 2) {
-              mbar_arrive(full);
+              if (leader) mbar_arrive(full);
             } else {
-              mbar_expect_tx(full, tx_bytes);
+              if (leader) mbar_expect_tx(full, tx_bytes);
               const uint32_t sa = stage0 + stage * p.stage_bytes;
 #pragma unroll
               for (int pl = 0; pl < PLANES; ++pl) {
                 const int q = pl * p.nchunk + chunk;  // (plane, K-block) image of the operand tensor
-                tma_load_5d(sa + pl * kABytes, &tmA, full, 0, cw, ch, s1 ? q : q * 4 + cp, n0);
+                if constexpr (CTA2)
+                  tma_load_5d_2sm(sa + pl * kABytes, &tmA, full, 0, cw, ch, s1 ? q : q * 4 + cp, n0);
+                else
+                  tma_load_5d(sa + pl * kABytes, &tmA, full, 0, cw, ch, s1 ? q : q * 4 + cp, n0);
 #pragma unroll
-                for (int half = 0; half < NB; ++half)
-                  tma_load_2d(sa + b_off + pl * p.b_plane_bytes + half * p.CB * 64, &tmB, full, 0,
-                              brow + pl * p.Cout + half * p.CB);
+                for (int half = 0; half < NB; ++half) {
+                  const uint32_t dst = sa + b_off + pl * p.b_plane_bytes + half * cbh * 64;
+                  const int row = brow + pl * p.Cout + half * p.CB + (CTA2 ? (int)rank * cbh : 0);
+                  if constexpr (CTA2)
+                    tma_load_2d_2sm(dst, &tmB, full, 0, row);
+                  else
+                    tma_load_2d(dst, &tmB, full, 0, row);
+                }
               }
             }
           }
@@ -360,15 +433,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================================================================== MMA issuer
     // Descriptor lo words are base + compile-time offsets, so a K-block is a straight run of
     // PLANES == 2 ? 6 : 2 (x NB) tcgen05.mma with no address arithmetic in between.
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.CB >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.CB >> 3) << 17) |
+                           (((CTA2 ? 256u : 128u) >> 4) << 24);
     const uint32_t lo0 = ((stage0 & 0x3FFFFu) >> 4) | (1u << 16);
-    const uint32_t stage_u = p.stage_bytes >> 4, bplane_u = p.b_plane_bytes >> 4, half_u = (uint32_t)(p.CB * 64) >> 4;
+    const uint32_t stage_u = p.stage_bytes >> 4, bplane_u = p.b_plane_bytes >> 4;
+    const uint32_t half_u = (uint32_t)((CTA2 ? p.CB / 2 : p.CB) * 64) >> 4;
     const uint32_t CB = (uint32_t)p.CB;
     const bool no_mma = (p.debug & 1) != 0;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
+    // in CTA2 mode only the leader issues (for both CTAs); the peer's MMA warp idles
+    for (int tile = tile_begin; leader && tile < tile_end; tile += gridDim.x, ++it) {
       const int acc = it % p.acc_stages;
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -389,14 +465,24 @@ __global__ void __launch_bounds__(kThreads, 1)
                 const uint32_t al = a_lo + (pass == 2 ? (kABytes >> 4) : 0u) + kk * 2;
                 const uint32_t bl = b_lo + (pass == 1 ? bplane_u : 0u) + kk * 2;
 #pragma unroll
-                for (int half = 0; half < NB; ++half)
-                  umma_bf16(d0 + half * CB, desc64(al), desc64(bl + half * half_u), idesc,
-                            (kk | pass) ? 1u : (uint32_t)(kb != 0));
+                for (int half = 0; half < NB; ++half) {
+                  if constexpr (CTA2)
+                    umma_bf16_2sm(d0 + half * CB, desc64(al), desc64(bl + half * half_u), idesc,
+                                  (kk | pass) ? 1u : (uint32_t)(kb != 0));
+                  else
+                    umma_bf16(d0 + half * CB, desc64(al), desc64(bl + half * half_u), idesc,
+                              (kk | pass) ? 1u : (uint32_t)(kb != 0));
+                }
               }
             }
           }
-          umma_commit(bar_empty + 8 * stage);
-          if (kb == kblocks - 1) umma_commit(bar_tfull + 8 * acc);
+          if constexpr (CTA2) {
+            umma_commit_2sm(bar_empty + 8 * stage);
+            if (kb == kblocks - 1) umma_commit_2sm(bar_tfull + 8 * acc);
+          } else {
+            umma_commit(bar_empty + 8 * stage);
+            if (kb == kblocks - 1) umma_commit(bar_tfull + 8 * acc);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) stage = 0, phase ^= 1;
@@ -409,7 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
     int it = 0;
     int sbuf = 0;  // staging set of the next 32-channel block (running over tiles)
-    for (int tile = blockIdx.x; tile < p.g.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
       const int acc = it % p.acc_stages;
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
       int n0, h0, w0;
@@ -525,7 +611,12 @@ __global__ void __launch_bounds__(kThreads, 1)
             // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+            if (lane == 0) {
+              if constexpr (CTA2)
+                mbar_arrive_leader(bar_tempty + 8 * acc);
+              else
+                mbar_arrive(bar_tempty + 8 * acc);
+            }
           }
           if (ln == 2) {
             // backward of the LayerNorm: gx = res + (g - mean g - a sum(g a)/(C-1)) rstd
@@ -613,7 +704,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if constexpr (CTA2)
+          mbar_arrive_leader(bar_tempty + 8 * acc);
+        else
+          mbar_arrive(bar_tempty + 8 * acc);
+      }
     }
     if (p.staged && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -622,8 +718,12 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if constexpr (CTA2) cluster_sync_all();  // neither CTA frees TMEM or exits while the pair is still working
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -681,7 +781,9 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_REQUIRE(c.Cout % 32 == 0, "C_out above 256 must be a multiple of 32");
     p.CB = c.Cout / 2, p.nb = 2, p.acc_stages = 1;
   }
-  p.b_plane_bytes = (uint32_t)round_up(c.Cout * 64, 1024);
+  static const int cta2_env = getenv("SDAB_UMMA_CTA2") ? atoi(getenv("SDAB_UMMA_CTA2")) : 1;
+  const bool cta2 = cta2_env != 0 && c.Cout % 32 == 0;  // each CTA holds C_out / 2 weight rows (multiple of 16)
+  p.b_plane_bytes = (uint32_t)round_up((cta2 ? c.Cout / 2 : c.Cout) * 64, 1024);
   p.stage_bytes = p.planes * (kABytes + p.b_plane_bytes);
   p.staged = c.Cout % 32 == 0;
   p.out_chunks = c.Cout / 32;
@@ -689,7 +791,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(!c.epi.ln || p.staged, "the fused LayerNorm epilogue needs C_out % 32 == 0");
   SDAB_REQUIRE(c.epi.ln != 2 || (c.epi.ln_a && c.epi.ln_rstd_in && !c.epi.bias && !c.epi.act && !c.epi.dact),
                "invalid backward-LayerNorm epilogue");
-  p.sbufs = !p.staged ? 1 : (c.Cout <= 128 ? 3 : (c.Cout <= 256 ? 2 : 1));
+  p.sbufs = 1;  // measured: deeper store staging does not pay for the ring stages it costs
   if (getenv("SDAB_UMMA_SBUFS")) p.sbufs = atoi(getenv("SDAB_UMMA_SBUFS"));
   SDAB_REQUIRE(p.sbufs >= 1 && p.sbufs <= 3, "staging sets out of range");
   p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - p.sbufs * kStagingBytes) / p.stage_bytes);
@@ -722,7 +824,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   {
     const cuuint64_t dims[2] = {32, (cuuint64_t)9 * p.nchunk * 2 * c.Cout};
     const cuuint64_t strides[1] = {64};
-    const cuuint32_t box[2] = {32, (cuuint32_t)p.CB};
+    const cuuint32_t box[2] = {32, (cuuint32_t)(cta2 ? p.CB / 2 : p.CB)};
     SDAB_TRY(encode(&tmB, c.wpk, 2, dims, strides, box));
   }
 
@@ -745,22 +847,38 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
 
   const size_t smem = kCtrlBytes + 1024 + (size_t)p.sbufs * kStagingBytes + (size_t)p.stages * p.stage_bytes;
   using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, UmmaParams);
-  static const Kernel kernels[2][2][3] = {
-      {{conv_umma_kernel<1, 1, 0>, conv_umma_kernel<1, 1, 1>, conv_umma_kernel<1, 1, 2>},
-       {conv_umma_kernel<1, 2, 0>, conv_umma_kernel<1, 2, 1>, conv_umma_kernel<1, 2, 2>}},
-      {{conv_umma_kernel<2, 1, 0>, conv_umma_kernel<2, 1, 1>, conv_umma_kernel<2, 1, 2>},
-       {conv_umma_kernel<2, 2, 0>, conv_umma_kernel<2, 2, 1>, conv_umma_kernel<2, 2, 2>}}};
+#define SDAB_K(P, B, L) {conv_umma_kernel<P, B, L, false>, conv_umma_kernel<P, B, L, true>}
+  static const Kernel kernels[2][2][3][2] = {{{SDAB_K(1, 1, 0), SDAB_K(1, 1, 1), SDAB_K(1, 1, 2)},
+                                             {SDAB_K(1, 2, 0), SDAB_K(1, 2, 1), SDAB_K(1, 2, 2)}},
+                                            {{SDAB_K(2, 1, 0), SDAB_K(2, 1, 1), SDAB_K(2, 1, 2)},
+                                             {SDAB_K(2, 2, 0), SDAB_K(2, 2, 1), SDAB_K(2, 2, 2)}}};
+#undef SDAB_K
   static bool attr_set = false;
   if (!attr_set) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         for (int l = 0; l < 3; ++l)
-          SDAB_CUDA_CHECK(cudaFuncSetAttribute(kernels[a][b][l], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+          for (int t = 0; t < 2; ++t)
+            SDAB_CUDA_CHECK(
+                cudaFuncSetAttribute(kernels[a][b][l][t], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   SDAB_REQUIRE(c.epi.ln >= 0 && c.epi.ln <= 2, "unknown fused LayerNorm variant");
-  const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
-  kernels[p.planes - 1][p.nb - 1][c.epi.ln]<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
+  const Kernel kernel = kernels[p.planes - 1][p.nb - 1][c.epi.ln][cta2 ? 1 : 0];
+  if (cta2) {
+    const int pairs = (p.g.num_tiles + 1) / 2;
+    const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    SDAB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmF, tmO, p));
+  } else {
+    const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
+    kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
+  }
   SDAB_LAUNCH_CHECK("conv_umma_kernel");
   return SDAB_OK;
 }
