@@ -30,8 +30,8 @@ constexpr int kTS = kTile + 2 * kHalo;
 __device__ __forceinline__ float face_value(float cl, float c, float cr, float cn, float uf, float dt_h) {
   const float d = cr - c;
   const float den = d != 0.f ? d : 1.f;
-  const float r = uf > 0.f ? (c - cl) / den : (cn - cr) / den;
-  const float phi = r > 0.f ? (2.f * r) / (1.f + r) : 0.f;
+  const float r = __fdividef(uf > 0.f ? c - cl : cn - cr, den);
+  const float phi = r > 0.f ? __fdividef(2.f * r, 1.f + r) : 0.f;
   const float upwind = uf > 0.f ? c : cr;
   const float courant = dt_h * uf;
   const float high = uf > 0.f ? c + 0.5f * (1.f - courant) * d : cr - 0.5f * (1.f + courant) * d;
@@ -39,10 +39,14 @@ __device__ __forceinline__ float face_value(float cl, float c, float cr, float c
 }
 
 // One forward-Euler update of the explicit terms.  grid: (N/32, N/32, E), block: (32, 8).
+// Each thread owns 4 consecutive rows of one column: the flux through the lower x face of a cell is
+// the upper-face flux of the previous row (carried in a register) and the flux through its left
+// y face comes from the neighbouring lane (warp shuffle), so every face flux is evaluated once.
 __global__ void __launch_bounds__(256)
     explicit_step_kernel(const float* __restrict__ uv, float* __restrict__ uvs, int N, float dt, float h, float nu) {
   __shared__ float su[kTS][kTS + 1];
   __shared__ float sv[kTS][kTS + 1];
+  __shared__ float sforce[kTile];
   const int e = blockIdx.z;
   const float* u = uv + (size_t)e * 2 * N * N;
   const float* v = u + (size_t)N * N;
@@ -54,42 +58,50 @@ __global__ void __launch_bounds__(256)
     su[li][lj] = u[(size_t)gi * N + gj];
     sv[li][lj] = v[(size_t)gi * N + gj];
   }
+  // Kolmogorov forcing sin(4 y) at u's offset y_{j+1/2} (constant along x)
+  if (threadIdx.y == 0) sforce[threadIdx.x] = sinf(4.f * ((float)(j0 + threadIdx.x) + 0.5f) * h);
   __syncthreads();
   const float dt_h = dt / h, inv_h = 1.f / h, inv_h2 = 1.f / (h * h);
   const int lj = threadIdx.x + kHalo;
-  for (int r = threadIdx.y; r < kTile; r += 8) {
+  const int lane = threadIdx.x;
+  float* us = uvs + (size_t)e * 2 * N * N;
+  float fxu_prev = 0.f, fxv_prev = 0.f;
+#pragma unroll
+  for (int k = -1; k < 4; ++k) {
+    // k = -1 only produces the x-face fluxes below the first owned row
+    const int r = 4 * threadIdx.y + k;
     const int li = r + kHalo;
-    const int gi = i0 + r, gj = j0 + threadIdx.x;
 #define U(di, dj) su[li + (di)][lj + (dj)]
 #define V(di, dj) sv[li + (di)][lj + (dj)]
-    // ---- u component (offset (1, 1/2))
-    float fxp, fxm, fyp, fym;
-    {
-      const float ufp = 0.5f * (U(0, 0) + U(1, 0)), ufm = 0.5f * (U(-1, 0) + U(0, 0));
-      fxp = face_value(U(-1, 0), U(0, 0), U(1, 0), U(2, 0), ufp, dt_h) * ufp;
-      fxm = face_value(U(-2, 0), U(-1, 0), U(0, 0), U(1, 0), ufm, dt_h) * ufm;
-      const float vfp = 0.5f * (V(0, 0) + V(1, 0)), vfm = 0.5f * (V(0, -1) + V(1, -1));
-      fyp = face_value(U(0, -1), U(0, 0), U(0, 1), U(0, 2), vfp, dt_h) * vfp;
-      fym = face_value(U(0, -2), U(0, -1), U(0, 0), U(0, 1), vfm, dt_h) * vfm;
+    // fluxes through the upper x face (between rows r and r + 1)
+    const float ufu = 0.5f * (U(0, 0) + U(1, 0));  // u at (3/2, 1/2) for the u equation
+    const float fxu = face_value(U(-1, 0), U(0, 0), U(1, 0), U(2, 0), ufu, dt_h) * ufu;
+    const float ufv = 0.5f * (U(0, 0) + U(0, 1));  // u at (1, 1) for the v equation
+    const float fxv = face_value(V(-1, 0), V(0, 0), V(1, 0), V(2, 0), ufv, dt_h) * ufv;
+    if (k >= 0) {
+      // fluxes through the right y face (between columns j and j + 1); the left one from lane - 1
+      const float vfu = 0.5f * (V(0, 0) + V(1, 0));  // v at (1, 1) for the u equation
+      const float fyu = face_value(U(0, -1), U(0, 0), U(0, 1), U(0, 2), vfu, dt_h) * vfu;
+      const float vfv = 0.5f * (V(0, 0) + V(0, 1));  // v at (1/2, 3/2) for the v equation
+      const float fyv = face_value(V(0, -1), V(0, 0), V(0, 1), V(0, 2), vfv, dt_h) * vfv;
+      float fyu_m = __shfl_up_sync(0xffffffffu, fyu, 1), fyv_m = __shfl_up_sync(0xffffffffu, fyv, 1);
+      if (lane == 0) {
+        const float vfu_m = 0.5f * (V(0, -1) + V(1, -1));
+        fyu_m = face_value(U(0, -2), U(0, -1), U(0, 0), U(0, 1), vfu_m, dt_h) * vfu_m;
+        const float vfv_m = 0.5f * (V(0, -1) + V(0, 0));
+        fyv_m = face_value(V(0, -2), V(0, -1), V(0, 0), V(0, 1), vfv_m, dt_h) * vfv_m;
+      }
+      const float conv_u = -((fxu - fxu_prev) + (fyu - fyu_m)) * inv_h;
+      const float lap_u = (U(1, 0) + U(-1, 0) + U(0, 1) + U(0, -1) - 4.f * U(0, 0)) * inv_h2;
+      const float force_u = sforce[lane] - 0.1f * U(0, 0);
+      const float conv_v = -((fxv - fxv_prev) + (fyv - fyv_m)) * inv_h;
+      const float lap_v = (V(1, 0) + V(-1, 0) + V(0, 1) + V(0, -1) - 4.f * V(0, 0)) * inv_h2;
+      const float force_v = -0.1f * V(0, 0);
+      const int gi = i0 + r, gj = j0 + lane;
+      us[(size_t)gi * N + gj] = U(0, 0) + dt * (conv_u + nu * lap_u + force_u);
+      us[(size_t)N * N + (size_t)gi * N + gj] = V(0, 0) + dt * (conv_v + nu * lap_v + force_v);
     }
-    const float conv_u = -((fxp - fxm) + (fyp - fym)) * inv_h;
-    const float lap_u = (U(1, 0) + U(-1, 0) + U(0, 1) + U(0, -1) - 4.f * U(0, 0)) * inv_h2;
-    const float force_u = sinf(4.f * ((float)gj + 0.5f) * h) - 0.1f * U(0, 0);
-    // ---- v component (offset (1/2, 1))
-    {
-      const float ufp = 0.5f * (U(0, 0) + U(0, 1)), ufm = 0.5f * (U(-1, 0) + U(-1, 1));
-      fxp = face_value(V(-1, 0), V(0, 0), V(1, 0), V(2, 0), ufp, dt_h) * ufp;
-      fxm = face_value(V(-2, 0), V(-1, 0), V(0, 0), V(1, 0), ufm, dt_h) * ufm;
-      const float vfp = 0.5f * (V(0, 0) + V(0, 1)), vfm = 0.5f * (V(0, -1) + V(0, 0));
-      fyp = face_value(V(0, -1), V(0, 0), V(0, 1), V(0, 2), vfp, dt_h) * vfp;
-      fym = face_value(V(0, -2), V(0, -1), V(0, 0), V(0, 1), vfm, dt_h) * vfm;
-    }
-    const float conv_v = -((fxp - fxm) + (fyp - fym)) * inv_h;
-    const float lap_v = (V(1, 0) + V(-1, 0) + V(0, 1) + V(0, -1) - 4.f * V(0, 0)) * inv_h2;
-    const float force_v = -0.1f * V(0, 0);
-    float* us = uvs + (size_t)e * 2 * N * N;
-    us[(size_t)gi * N + gj] = U(0, 0) + dt * (conv_u + nu * lap_u + force_u);
-    us[(size_t)N * N + (size_t)gi * N + gj] = V(0, 0) + dt * (conv_v + nu * lap_v + force_v);
+    fxu_prev = fxu, fxv_prev = fxv;
 #undef U
 #undef V
   }
@@ -331,7 +343,7 @@ int project(const sdab_kolmogorov* k, const float* src, float* dst, float2* spec
   const size_t row_smem = (size_t)(N / 2 + kRows * N) * sizeof(float2);
   div_row_fft_kernel<<<dim3(N / kRows, npairs), dim3(N / 2, kRows), row_smem, st>>>(src, spec, N, E, k->h, 0);
   SDAB_LAUNCH_CHECK("div_row_fft_kernel");
-  const int CT = N <= 256 ? 4 : 2;
+  const int CT = N <= 256 ? 8 : 2;
   const size_t col_smem = (size_t)(N / 2 + CT * (N + 1)) * sizeof(float2);
   col_solve_kernel<<<dim3(N / CT, npairs), dim3(CT, N / 2), col_smem, st>>>(spec, N, k->log2n, CT, k->h, 0);
   SDAB_LAUNCH_CHECK("col_solve_kernel");
@@ -410,7 +422,7 @@ int sdab_kolmogorov_prior(sdab_kolmogorov* k, float* uv, int E, uint64_t seed, v
   const size_t row_smem = (size_t)(N / 2 + kRows * N) * sizeof(float2);
   div_row_fft_kernel<<<dim3(N / kRows, E), dim3(N / 2, kRows), row_smem, st>>>(w.uvs, w.spec, N, E, k->h, 1);
   SDAB_LAUNCH_CHECK("div_row_fft_kernel");
-  const int CT = N <= 256 ? 4 : 2;
+  const int CT = N <= 256 ? 8 : 2;
   const size_t col_smem = (size_t)(N / 2 + CT * (N + 1)) * sizeof(float2);
   col_solve_kernel<<<dim3(N / CT, E), dim3(CT, N / 2), col_smem, st>>>(w.spec, N, k->log2n, CT, k->h, 1);
   SDAB_LAUNCH_CHECK("col_solve_kernel");
