@@ -147,13 +147,28 @@ struct ConvEpilogue {
   const float* ln_rstd_in; // backward: saved rstd per pixel
 };
 
+// Explicit tap list of a convolution launch (n == 0 selects the default 3x3 list).  Tap t reads the
+// TMA box at row / column offsets (ca, cb) of the haloed operand image (parity image cp when the
+// input is in the S2 layout) and multiplies it with tap `wtap` of the packed weights.  This covers
+// the 3x3 conv, the stride-2 heads, the sub-pixel form of "nearest x2 -> conv" (4 taps per output
+// parity), its transpose (a 4x4 stride-2 conv, 16 taps) and the parity classes of the head transposes.
+struct ConvTaps {
+  int n;
+  unsigned char ca[16], cb[16], cp[16], wtap[16];
+};
+
 struct ConvProblem {
-  const bf16* in;      // OP(Cin) at resolution (H*stride, W*stride); S2 layout iff stride == 2
+  const bf16* in;      // OP(Cin) at resolution (H*stride, W*stride); S2 layout iff stride == 2 or in_s2
   const bf16* wpk;     // packed weights [9][Cin/32][2][Cout][32]
   int N, H, W;         // OUTPUT resolution
   int Cin, Cout;       // padded: Cin % 32 == 0, Cout % 16 == 0
   int stride;          // 1 or 2
   int mode;            // SDAB_MODE_*
+  int in_s2;           // input operand in the parity layout of a (2H) x (2W) image (implied by stride == 2)
+  ConvTaps taps;       // explicit taps (tcgen05 engine only), or n == 0
+  int wtaps;           // taps in the packed weight array (0 means 9)
+  int os, oh0, ow0;    // output placement (tcgen05 engine only): GEMM pixel (h, w) is pixel (os h + oh0, os w + ow0)
+                       // of an (os H) x (os W) output image; os == 0 means 1
   double flops;        // algorithmic FLOPs of this launch (2 * pixels * 9 * C_in,real * C_out,real), for profiling
   ConvEpilogue epi;
 };
@@ -236,6 +251,7 @@ int ln_backward(const float* ga, const bf16* a_op, const float* rstd, const floa
 int time_shifts(const float* y, const float* pw, const float* pb, float* out, int Nt, int rows, int mod,
                 cudaStream_t st);
 int pack_conv_weights(const float* w, bf16* fwd, bf16* bwd, int Cout, int Cin, cudaStream_t st);
+int pack_tail_weights(const float* w, bf16* tf, bf16* tb, int Cout, int Cin, cudaStream_t st);
 int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);
 

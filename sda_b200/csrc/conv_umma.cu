@@ -46,6 +46,10 @@ struct UmmaParams {
   int stages, acc_stages;
   int CB, nb;      // N of one MMA, number of N halves
   uint32_t b_plane_bytes, stage_bytes;
+  int in_s2;       // A operand in the parity layout
+  int ntaps;
+  uint32_t tap[16];  // ca | cb << 8 | cp << 16 | wtap << 24
+  int os, oh0, ow0, Ho, Wo;  // output placement (ConvProblem::os ...) and output image size
   int staged;      // epilogue through shared memory + TMA stores (C_out % 32 == 0)
   int sbufs;       // number of staging sets (TMA stores in flight behind the epilogue)
   int out_chunks;  // C_out / 32
@@ -196,6 +200,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3,
@@ -374,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int kblocks = 9 * p.nchunk;
+  const int kblocks = p.ntaps * p.nchunk;
   const uint32_t acc_stride = p.acc_stages == 2 ? 256u : 0u;
   constexpr uint32_t b_off = PLANES * kABytes;
 
@@ -387,15 +396,14 @@ __global__ void __launch_bounds__(kThreads, 1)
     // also receives the peer's bytes
     const int cbh = CTA2 ? p.CB / 2 : p.CB;  // B rows of one N half held by this CTA
     const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * PLANES * (kABytes + (uint32_t)(NB * cbh) * 64u);
-    const bool s1 = p.stride == 1;
+    const bool s1 = !p.in_s2;
     for (int tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       int n0, h0, w0;
       p.g.tile_origin(tile, n0, h0, w0);
-      int brow = 0;
-      for (int tap = 0; tap < 9; ++tap) {
-        const int a = tap / 3, b = tap - 3 * a;
-        const int cw = s1 ? w0 + b : w0 + (b >> 1), ch = s1 ? h0 + a : h0 + (a >> 1);
-        const int cp = s1 ? 0 : (a & 1) * 2 + (b & 1);
+      for (int tap = 0; tap < p.ntaps; ++tap) {
+        const uint32_t tp = p.tap[tap];
+        const int ch = h0 + (int)(tp & 255u), cw = w0 + (int)((tp >> 8) & 255u), cp = (int)((tp >> 16) & 255u);
+        int brow = (int)(tp >> 24) * p.nchunk * 2 * p.Cout;
         for (int chunk = 0; chunk < p.nchunk; ++chunk, brow += 2 * p.Cout) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           if (elect_one()) {
@@ -500,9 +508,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
       int n0, h0, w0;
       p.g.tile_origin(tile, n0, h0, w0);
-      const int n = n0 + bn, h = h0 + bh, w = w0 + bw;
+      // (h, w): output pixel of this thread in the (Ho x Wo) output image (ConvProblem::os, oh0, ow0)
+      const int n = n0 + bn, h = p.os * (h0 + bh) + p.oh0, w = p.os * (w0 + bw) + p.ow0;
       const bool valid = n < p.N;
-      const size_t pix = ((size_t)n * p.H + h) * p.W + w;
+      const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
@@ -512,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int c0 = 0; c0 < p.Cout; c0 += 16) {
           float v[16];
           tmem_ld16(t0 + c0, v);
-          if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.H, p.W, p.Cout, c0);
+          if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.Ho, p.Wo, p.Cout, c0);
         }
       } else {
         // Staged epilogue: every output leaves the SM as full cache lines.  Per 32-channel block the
@@ -520,9 +529,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         // then issues TMA stores (F: [pixels][C] matrix, OP: the (plane, K-block) image box).
         const bool wantF = p.epi.outF != nullptr || p.epi.pre != nullptr;
         const bool wantO = p.epi.outOP != nullptr;
-        const size_t pix0 = ((size_t)n0 * p.H + h0) * p.W + w0;
-        const bool edge = valid && (h == 0 || h == p.H - 1 || w == 0 || w == p.W - 1);
-        const OpShape so{0, p.H, p.W, p.Cout, 0};
+        const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
+        const OpShape so{0, p.Ho, p.Wo, p.Cout, 0};
         constexpr int ln = LN;  // fused LayerNorm variant (ConvEpilogue::ln), compile-time to keep registers down
         // developer ablation bits: 8 = no LayerNorm statistics pass, 16 = no global operand loads, 32 = no stores
         const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
@@ -532,9 +540,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (nt < p.g.num_tiles) {
             int nn0, nh0, nw0;
             p.g.tile_origin(nt, nn0, nh0, nw0);
-            const int nn = nn0 + bn, nh = nh0 + bh, nw = nw0 + bw;
+            const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
             if (nn < p.N) {
-              const size_t npix = ((size_t)nn * p.H + nh) * p.W + nw;
+              const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
               const float* pf = p.epi.res ? p.epi.res : p.epi.dact;
               if (pf)
                 for (int c = 0; c < p.Cout; c += 32) prefetch_l2(pf + npix * p.Cout + c);
@@ -672,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               // halo replicas of edge pixels (the TMA box covers the interior position only)
               const size_t blk = (size_t)cc * so.block_stride(), lo_off = so.lo_offset();
               bool first = true;
-              for_each_replica(h, w, p.H, p.W, [&](int hp, int wp) {
+              for_each_replica(h, w, p.Ho, p.Wo, [&](int hp, int wp) {
                 if (first) {
                   first = false;
                   return;
@@ -691,10 +699,11 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (threadIdx.x == 64 && !(p.debug & 128)) {
             // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
             // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
-            if (wantF) tma_store_2d(&tmF, staging, cc * 32, (int)pix0);
+            // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
+            if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
             if (wantO) {
-              tma_store_5d(&tmO, staging + kStageF, 0, w0 + 1, h0 + 1, cc, n0);
-              tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0 + 1, h0 + 1, p.out_chunks + cc, n0);
+              tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
+              tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + cc, n0);
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -773,6 +782,26 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(c.Cout % 16 == 0 && c.Cout >= 16 && c.Cout <= 512, "C_out must be a multiple of 16, at most 512");
   SDAB_REQUIRE(c.stride == 1 || c.stride == 2, "stride must be 1 or 2");
   p.N = c.N, p.H = c.H, p.W = c.W, p.Cin = c.Cin, p.Cout = c.Cout, p.stride = c.stride;
+  p.in_s2 = c.stride == 2 || c.in_s2;
+  p.os = c.os ? c.os : 1, p.oh0 = c.oh0, p.ow0 = c.ow0;
+  SDAB_REQUIRE((p.os == 1 && !p.oh0 && !p.ow0) || (p.os == 2 && p.oh0 >= 0 && p.oh0 < 2 && p.ow0 >= 0 && p.ow0 < 2),
+               "invalid output placement");
+  p.Ho = p.os * c.H, p.Wo = p.os * c.W;
+  if (c.taps.n) {
+    SDAB_REQUIRE(c.taps.n >= 1 && c.taps.n <= 16, "tap list out of range");
+    p.ntaps = c.taps.n;
+    for (int t = 0; t < p.ntaps; ++t)
+      p.tap[t] = (uint32_t)c.taps.ca[t] | ((uint32_t)c.taps.cb[t] << 8) | ((uint32_t)c.taps.cp[t] << 16) |
+                 ((uint32_t)c.taps.wtap[t] << 24);
+  } else {
+    p.ntaps = 9;
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b)
+        p.tap[3 * a + b] = p.in_s2 ? ((uint32_t)(a >> 1) | ((uint32_t)(b >> 1) << 8) |
+                                      ((uint32_t)((a & 1) * 2 + (b & 1)) << 16) | ((uint32_t)(3 * a + b) << 24))
+                                   : ((uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(3 * a + b) << 24));
+  }
+  const int wtaps = c.wtaps ? c.wtaps : 9;
   p.nchunk = c.Cin / 32;
   p.planes = c.mode == SDAB_MODE_BF16X3 ? 2 : 1;
   if (c.Cout <= 256) {
@@ -804,12 +833,12 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   }
 
   // A: haloed operand tensor at the input resolution, [N][2 * C/32][Hp][Wp][32] (common.cuh)
-  const int Hin = c.H * c.stride, Win = c.W * c.stride;
+  const int Hin = p.in_s2 ? 2 * c.H : c.H, Win = p.in_s2 ? 2 * c.W : c.W;
   const cuuint64_t Hp = Hin + 2, Wp = Win + 2, Q = 2 * (cuuint64_t)p.nchunk;
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5], strides[4];
-    if (c.stride == 1) {
+    if (!p.in_s2) {
       dims[0] = 32, dims[1] = Wp, dims[2] = Hp, dims[3] = Q, dims[4] = (cuuint64_t)c.N;
       strides[0] = 64, strides[1] = Wp * 64, strides[2] = Hp * Wp * 64, strides[3] = Q * Hp * Wp * 64;
     } else {
@@ -822,27 +851,31 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_TRY(encode(&tmA, c.in, 5, dims, strides, box));
   }
   {
-    const cuuint64_t dims[2] = {32, (cuuint64_t)9 * p.nchunk * 2 * c.Cout};
+    const cuuint64_t dims[2] = {32, (cuuint64_t)wtaps * p.nchunk * 2 * c.Cout};
     const cuuint64_t strides[1] = {64};
     const cuuint32_t box[2] = {32, (cuuint32_t)(cta2 ? p.CB / 2 : p.CB)};
     SDAB_TRY(encode(&tmB, c.wpk, 2, dims, strides, box));
   }
 
-  // epilogue outputs (staged path): F as the [pixels][C_out] fp32 matrix, OP as its haloed images
+  // epilogue outputs (staged path).  F: [N * H][W][C_out] view of the fp32 output image with the
+  // placement stride / offset folded into the strides / base; OP: the haloed (plane, K-block) images,
+  // base at the first interior pixel.  A tile is then one box at (channel block, w0, n0 * H + h0).
   CUtensorMap tmF = tmB, tmO = tmB;
   if (p.staged && (c.epi.outF || c.epi.pre)) {
-    const cuuint64_t dims[2] = {(cuuint64_t)c.Cout, (cuuint64_t)c.N * c.H * c.W};
-    const cuuint64_t strides[1] = {(cuuint64_t)c.Cout * 4};
-    const cuuint32_t box[2] = {32, 128};
-    SDAB_TRY(encode(&tmF, c.epi.outF ? c.epi.outF : c.epi.pre, 2, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
-                    CU_TENSOR_MAP_SWIZZLE_128B));
+    float* basep = (c.epi.outF ? c.epi.outF : c.epi.pre) + ((size_t)p.oh0 * p.Wo + p.ow0) * c.Cout;
+    const cuuint64_t dims[3] = {(cuuint64_t)c.Cout, (cuuint64_t)c.W, (cuuint64_t)c.N * c.H};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.os * c.Cout * 4, (cuuint64_t)p.os * p.Wo * c.Cout * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)p.g.BW, (cuuint32_t)(p.g.BH * p.g.BN)};
+    SDAB_TRY(encode(&tmF, basep, 3, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B));
   }
   if (p.staged && c.epi.outOP) {
-    const cuuint64_t Ho = c.H + 2, Wo = c.W + 2, Qo = 2 * (cuuint64_t)p.out_chunks;
-    const cuuint64_t dims[5] = {32, Wo, Ho, Qo, (cuuint64_t)c.N};
-    const cuuint64_t strides[4] = {64, Wo * 64, Ho * Wo * 64, Qo * Ho * Wo * 64};
+    const cuuint64_t Hpo = p.Ho + 2, Wpo = p.Wo + 2, Qo = 2 * (cuuint64_t)p.out_chunks;
+    const bf16* basep = c.epi.outOP + ((size_t)(p.oh0 + 1) * Wpo + (p.ow0 + 1)) * 32;
+    const cuuint64_t dims[5] = {32, (cuuint64_t)c.W, (cuuint64_t)c.H, Qo, (cuuint64_t)c.N};
+    const cuuint64_t strides[4] = {(cuuint64_t)p.os * 64, (cuuint64_t)p.os * Wpo * 64, Hpo * Wpo * 64,
+                                   Qo * Hpo * Wpo * 64};
     const cuuint32_t box[5] = {32, (cuuint32_t)p.g.BW, (cuuint32_t)p.g.BH, 1, (cuuint32_t)p.g.BN};
-    SDAB_TRY(encode(&tmO, c.epi.outOP, 5, dims, strides, box));
+    SDAB_TRY(encode(&tmO, basep, 5, dims, strides, box));
   }
 
   const size_t smem = kCtrlBytes + 1024 + (size_t)p.sbufs * kStagingBytes + (size_t)p.stages * p.stage_bytes;

@@ -332,6 +332,50 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, bf16* __re
   }
 }
 
+// Combined weights of a tail (LayerNorm -> nearest x2 -> 3x3 conv, sda/nn.py:161-170):
+//   tf[4 (po, pp) + 2 th + tw][chunk][plane][co][kc]: sub-pixel form -- output parity (po, pp) is a 2x2-tap
+//       conv of the LOW-resolution input with taps summed over S(po, th) x S(pp, tw),
+//       S(0,0) = {0}, S(0,1) = {1,2}, S(1,0) = {0,1}, S(1,1) = {2};
+//   tb[4 a + b][chunk][plane][ci][kc]: its transpose -- a 4x4 stride-2 conv of the padded high-resolution
+//       cotangent with taps summed over R(a) x R(b), R = {2}, {1,2}, {0,1}, {0}, channels transposed.
+__global__ void pack_tail_weights_kernel(const float* __restrict__ w, bf16* __restrict__ tf, bf16* __restrict__ tb,
+                                         int Cout, int Cin) {
+  const size_t nf = (size_t)16 * Cin * Cout, nb = nf;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (size_t)gridDim.x * blockDim.x) {
+    const bool is_b = i >= nf;
+    size_t j = is_b ? i - nf : i;
+    const int K = is_b ? Cout : Cin, Nn = is_b ? Cin : Cout;
+    const int kc = j % 32;
+    j /= 32;
+    const int row = j % Nn;
+    j /= Nn;
+    const int chunk = j % (K / 32);
+    const int tap = j / (K / 32);
+    const int k = chunk * 32 + kc;
+    const int co = is_b ? k : row, ci = is_b ? row : k;
+    // row / column tap sets as [first, last] ranges
+    int a0, a1, b0, b1;
+    if (!is_b) {
+      const int po = tap >> 3, pp = (tap >> 2) & 1, th = (tap >> 1) & 1, tw = tap & 1;
+      a0 = po ? (th ? 2 : 0) : (th ? 1 : 0), a1 = po ? (th ? 2 : 1) : (th ? 2 : 0);
+      b0 = pp ? (tw ? 2 : 0) : (tw ? 1 : 0), b1 = pp ? (tw ? 2 : 1) : (tw ? 2 : 0);
+    } else {
+      const int a = tap >> 2, b = tap & 3;
+      a0 = a == 0 ? 2 : (a == 1 ? 1 : 0), a1 = a == 0 ? 2 : (a == 1 ? 2 : (a == 2 ? 1 : 0));
+      b0 = b == 0 ? 2 : (b == 1 ? 1 : 0), b1 = b == 0 ? 2 : (b == 1 ? 2 : (b == 2 ? 1 : 0));
+    }
+    float v = 0.f;
+    for (int a = a0; a <= a1; ++a)
+      for (int b = b0; b <= b1; ++b) v += w[(((size_t)co * Cin + ci) * 3 + a) * 3 + b];
+    bf16 hi, lo;
+    split_bf16(v, hi, lo);
+    bf16* dst = is_b ? tb : tf;
+    const size_t base = (((size_t)tap * (K / 32) + chunk) * 2) * Nn * 32;
+    dst[base + (size_t)row * 32 + kc] = hi;
+    dst[base + (size_t)Nn * 32 + (size_t)row * 32 + kc] = lo;
+  }
+}
+
 __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
@@ -403,6 +447,13 @@ int time_shifts(const float* y, const float* pw, const float* pb, float* out, in
 int pack_conv_weights(const float* w, bf16* fwd, bf16* bwd, int Cout, int Cin, cudaStream_t st) {
   pack_conv_weights_kernel<<<296, 256, 0, st>>>(w, fwd, bwd, Cout, Cin);
   SDAB_LAUNCH_CHECK("pack_conv_weights_kernel");
+  return SDAB_OK;
+}
+
+int pack_tail_weights(const float* w, bf16* tf, bf16* tb, int Cout, int Cin, cudaStream_t st) {
+  SDAB_REQUIRE(Cout % 32 == 0 && Cin % 32 == 0, "tail channels must be multiples of 32");
+  pack_tail_weights_kernel<<<296, 256, 0, st>>>(w, tf, tb, Cout, Cin);
+  SDAB_LAUNCH_CHECK("pack_tail_weights_kernel");
   return SDAB_OK;
 }
 

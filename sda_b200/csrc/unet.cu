@@ -24,6 +24,8 @@ struct ConvLayer {
   int kf, nf;           // forward GEMM K (ceil32 cin), N (ceil16 cout)
   int kb, nb;           // backward GEMM K (ceil32 cout), N (ceil16 cin)
   size_t off_fwd, off_bwd, off_bias;  // byte offsets in the packed buffer
+  size_t off_tf = 0, off_tb = 0;      // tails (d > 0): combined sub-pixel / transposed 4x4 weights (16 taps each)
+  bool is_tail = false;
 };
 
 struct Arena {
@@ -211,12 +213,17 @@ int sdab_unet_create(const sdab_unet_desc* desc, sdab_unet** out) {
       h->asc_blk[d].push_back(add_block(C));
     }
     h->tail_conv[d] = add_conv(C, d == 0 ? desc->out_channels : desc->hidden_channels[d - 1]);
+    h->convs[h->tail_conv[d]].is_tail = d > 0;
   }
   Arena a;
   for (auto& c : h->convs) {
     c.off_fwd = a.take((size_t)9 * c.kf * c.nf * 2 * sizeof(bf16));
     c.off_bwd = a.take((size_t)9 * c.kb * c.nb * 2 * sizeof(bf16));
     c.off_bias = a.take((size_t)c.nf * sizeof(float));
+    if (c.is_tail) {
+      c.off_tf = a.take((size_t)16 * c.cin * c.cout * 2 * sizeof(bf16));
+      c.off_tb = a.take((size_t)16 * c.cin * c.cout * 2 * sizeof(bf16));
+    }
   }
   h->off_projw = a.take((size_t)h->shift_rows * desc->mod_features * sizeof(float));
   h->off_projb = a.take((size_t)h->shift_rows * sizeof(float));
@@ -250,6 +257,8 @@ int sdab_unet_set_weights(sdab_unet* h, const float* const* conv_w, const float*
   for (size_t i = 0; i < h->convs.size(); ++i) {
     const ConvLayer& c = h->convs[i];
     SDAB_TRY(pack_conv_weights(conv_w[i], (bf16*)(base + c.off_fwd), (bf16*)(base + c.off_bwd), c.cout, c.cin, st));
+    if (c.is_tail)
+      SDAB_TRY(pack_tail_weights(conv_w[i], (bf16*)(base + c.off_tf), (bf16*)(base + c.off_tb), c.cout, c.cin, st));
     SDAB_TRY(fill_zero(base + c.off_bias, (size_t)c.nf * sizeof(float), st));
     SDAB_TRY(copy_f32(conv_b[i], (float*)(base + c.off_bias), c.cout, st));
   }
@@ -381,7 +390,29 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       cur = dst;
     }
     const int ci = h->tail_conv[d];
-    if (d > 0) {
+    if (d > 0 && fuse) {
+      // tail = LN -> nearest x2 -> conv (sda/nn.py:161-170) in sub-pixel form: the LayerNorm output stays
+      // at the LOW resolution and each output parity (po, pp) is a 2x2-tap conv with summed weights
+      // (4 / 9 of the FLOPs, a quarter of the operand traffic)
+      SDAB_TRY(ln_forward(cur, nullptr, 0, 1, OP(p.upop[d]), save ? F(p.rstd_tail[d]) : nullptr, N, Hd, Wd, C, 0, st));
+      const int next_j = h->d.hidden_blocks[d - 1] > 0 ? h->asc_blk[d - 1][0] : -1;
+      for (int cls = 0; cls < 4; ++cls) {
+        const int po = cls >> 1, pp = cls & 1;
+        ConvProblem q{};
+        q.in = OP(p.upop[d]), q.wpk = (const bf16*)(pk + h->convs[ci].off_tf), q.wtaps = 16;
+        q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = h->d.hidden_channels[d - 1], q.stride = 1, q.mode = mode;
+        q.os = 2, q.oh0 = po, q.ow0 = pp;
+        q.taps.n = 4;
+        for (int t = 0; t < 4; ++t) {
+          q.taps.ca[t] = (unsigned char)(po + (t >> 1)), q.taps.cb[t] = (unsigned char)(pp + (t & 1));
+          q.taps.cp[t] = 0, q.taps.wtap[t] = (unsigned char)(cls * 4 + t);
+        }
+        q.epi.bias = bias(ci), q.epi.res = F(p.skip[d - 1]), q.epi.outF = F(p.x0[d - 1]);
+        fuse_ln(q, next_j);
+        SDAB_TRY(run_conv(engine, q, st));  // algorithmic FLOPs: the reference's 9 taps per high-resolution pixel
+      }
+      cur = F(p.x0[d - 1]);
+    } else if (d > 0) {
       SDAB_TRY(ln_forward(cur, nullptr, 0, 1, OP(p.upop[d]), save ? F(p.rstd_tail[d]) : nullptr, N, Hd, Wd, C, 1, st));
       ConvProblem q{};
       q.in = OP(p.upop[d]), q.wpk = wf(ci), q.N = N, q.H = 2 * Hd, q.W = 2 * Wd, q.Cin = C;
@@ -471,7 +502,27 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       SDAB_TRY(block_bwd(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst));
       cur = dst;
     }
-    if (d < D - 1) {
+    if (d < D - 1 && engine == SDAB_ENGINE_UMMA) {
+      // transpose of the sub-pixel tail: a 4x4 stride-2 conv of the cotangent (parity layout) with the
+      // summed, transposed weights, directly at the low resolution, LayerNorm adjoint fused
+      gskip[d] = cur;
+      const int ci = h->tail_conv[d + 1];
+      const int Cn = h->d.hidden_channels[d + 1];
+      SDAB_TRY(f_to_operand(cur, OP(p.xs2[d]), N, Hd, Wd, C, 1, st));
+      ConvProblem q{};
+      q.in = OP(p.xs2[d]), q.in_s2 = 1, q.wpk = (const bf16*)(pk + h->convs[ci].off_tb), q.wtaps = 16;
+      q.N = N, q.H = Hd / 2, q.W = Wd / 2, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
+      q.taps.n = 16;
+      for (int t = 0; t < 16; ++t) {
+        const int a = t >> 2, b = t & 3;
+        q.taps.ca[t] = (unsigned char)(a >> 1), q.taps.cb[t] = (unsigned char)(b >> 1);
+        q.taps.cp[t] = (unsigned char)((a & 1) * 2 + (b & 1)), q.taps.wtap[t] = (unsigned char)t;
+      }
+      q.epi.ln = 2, q.epi.ln_a = OP(p.upop[d + 1]), q.epi.ln_rstd_in = F(p.rstd_tail[d + 1]);
+      q.epi.outF = G0(d + 1), q.epi.outOP = GOP(d + 1);
+      SDAB_TRY(run_conv(engine, q, st, -1, -1, 4.0));  // algorithmic FLOPs are counted at the high resolution
+      cur = G0(d + 1);
+    } else if (d < D - 1) {
       gskip[d] = cur;
       const int ci = h->tail_conv[d + 1];
       const int Cn = h->d.hidden_channels[d + 1];
@@ -492,7 +543,29 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       cur = dst;
     }
     const int ci = h->head_conv[d];
-    if (d > 0) {
+    if (d > 0 && engine == SDAB_ENGINE_UMMA) {
+      // transpose of the stride-2 head by output parity: gx[2i + po, 2j + pp] only receives the taps
+      // with a = po + 1 (mod 2), b = pp + 1 (mod 2) -- 1, 2, 2 and 4 taps instead of 9 on a
+      // zero-upsampled cotangent
+      const int Cp = h->d.hidden_channels[d - 1];
+      float* dst = gskip[d - 1] == G0(d - 1) ? G1(d - 1) : G0(d - 1);
+      static const int off1[2][2] = {{1, -1}, {2, 1}}, wt1[2][2] = {{1, -1}, {2, 0}}, cnt1[2] = {1, 2};
+      for (int cls = 0; cls < 4; ++cls) {
+        const int po = cls >> 1, pp = cls & 1;
+        ConvProblem q{};
+        q.in = GOP(d), q.wpk = wb(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = Cp, q.stride = 1, q.mode = mode;
+        q.os = 2, q.oh0 = po, q.ow0 = pp;
+        q.taps.n = cnt1[po] * cnt1[pp];
+        for (int ta = 0, t = 0; ta < cnt1[po]; ++ta)
+          for (int tb = 0; tb < cnt1[pp]; ++tb, ++t) {
+            q.taps.ca[t] = (unsigned char)off1[po][ta], q.taps.cb[t] = (unsigned char)off1[pp][tb];
+            q.taps.cp[t] = 0, q.taps.wtap[t] = (unsigned char)(3 * wt1[po][ta] + wt1[pp][tb]);
+          }
+        q.epi.res = gskip[d - 1], q.epi.outF = dst, q.epi.outOP = GOP(d - 1);
+        SDAB_TRY(run_conv(engine, q, st, -1, -1, q.taps.n / 9.0));
+      }
+      cur = dst;
+    } else if (d > 0) {
       const int Cp = h->d.hidden_channels[d - 1];
       SDAB_TRY(f_to_operand(cur, OP(p.gz[d]), N, 2 * Hd, 2 * Wd, C, 2, st));
       float* dst = gskip[d - 1] == G0(d - 1) ? G1(d - 1) : G0(d - 1);
