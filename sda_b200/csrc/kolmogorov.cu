@@ -17,6 +17,8 @@
 //   col_solve       FFT along x, multiply by 1 / (lambda_x + lambda_y) / N^2, inverse FFT along x
 //   row_ifft        inverse FFT along y -> q (complex pair field)
 //   grad_sub        v = v* - grad q
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sdab {
@@ -305,6 +307,364 @@ __global__ void normalize_speed_kernel(float* __restrict__ uv, int N, float vmax
   for (int i = threadIdx.x; i < N * N; i += blockDim.x) u[i] *= scale, v[i] *= scale;
 }
 
+
+// ============================================================================================
+// Fast path (N = RX^2, RX in {8, 16}): three kernels per inner step, every FFT a two-pass
+// radix-RX transform held in registers (one shared-memory exchange per line instead of log2 N
+// synchronised radix-2 passes), and each streaming pass fused with its neighbours:
+//   fused_explicit_rowfft   u*, v* = v + dt F(v) for a slab of rows of BOTH members of a pair,
+//                           z = div(u*, v*)_a + i div(u*, v*)_b, FFT along y   (was 2 kernels)
+//   fused_col_solve         FFT along x, pseudo-inverse Laplacian, inverse FFT along x
+//   fused_rowifft_grad      inverse FFT along y, v = v* - grad q                (was 2 kernels)
+// Spectra are stored in natural frequency order (the two-pass split k = k1 + RX k2 lands there
+// without a permutation).  The host walks the ensemble in chunks whose working set stays in L2.
+// ============================================================================================
+__device__ __forceinline__ float2 operator+(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 operator-(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+
+// d * exp(SIGN 2 pi i k / 16), k a compile-time constant after unrolling
+template <int SIGN>
+__device__ __forceinline__ float2 mul_w16(float2 d, int k) {
+  constexpr float s = (float)SIGN;
+  switch (k) {
+    case 0: return d;
+    case 4: return make_float2(-s * d.y, s * d.x);
+    case 2: return make_float2(0.70710678118654752f * (d.x - s * d.y), 0.70710678118654752f * (s * d.x + d.y));
+    case 6: return make_float2(-0.70710678118654752f * (d.x + s * d.y), 0.70710678118654752f * (s * d.x - d.y));
+    case 1: return cmul(d, make_float2(0.92387953251128674f, s * 0.38268343236508977f));
+    case 3: return cmul(d, make_float2(0.38268343236508977f, s * 0.92387953251128674f));
+    case 5: return cmul(d, make_float2(-0.38268343236508977f, s * 0.92387953251128674f));
+    default: return cmul(d, make_float2(-0.92387953251128674f, s * 0.38268343236508977f));
+  }
+}
+
+template <int R, int HALF, int SIGN>
+__device__ __forceinline__ void fft_stage(float2 (&a)[R]) {
+#pragma unroll
+  for (int g = 0; g < R; g += 2 * HALF) {
+#pragma unroll
+    for (int pos = 0; pos < HALF; ++pos) {
+      const float2 x = a[g + pos], y = a[g + pos + HALF];
+      a[g + pos] = x + y;
+      a[g + pos + HALF] = mul_w16<SIGN>(x - y, pos * (8 / HALF));
+    }
+  }
+}
+
+// In-register DFT of R = 8 or 16 points, X[k] = sum_n a[n] exp(SIGN 2 pi i n k / R), natural order
+// in and out (the bit reversal of the decimation-in-frequency passes is a register renaming).
+template <int R, int SIGN>
+__device__ __forceinline__ void fft_reg(float2 (&a)[R]) {
+  static_assert(R == 8 || R == 16, "radix");
+  if constexpr (R == 16) fft_stage<R, 8, SIGN>(a);
+  fft_stage<R, 4, SIGN>(a);
+  fft_stage<R, 2, SIGN>(a);
+  fft_stage<R, 1, SIGN>(a);
+  float2 b[R];
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    int r = 0;
+#pragma unroll
+    for (int bit = 1, rb = R >> 1; bit < R; bit <<= 1, rb >>= 1)
+      if (k & bit) r |= rb;
+    b[k] = a[r];
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) a[k] = b[k];
+}
+
+// tw[m] = exp(-2 pi i m / N)
+__device__ __forceinline__ void fill_twiddles_full(float2* tw, int N, int tid, int nthreads) {
+  for (int m = tid; m < N; m += nthreads) {
+    float s, c;
+    sincospif(-2.f * (float)m / (float)N, &s, &c);
+    tw[m] = make_float2(c, s);
+  }
+}
+
+// Two-pass length-N = RX^2 transform of one line by RX cooperating threads (same warp, lanes
+// t = 0 .. RX-1 of an aligned group).  `x` is a line buffer of RX (RX + 1) float2.
+//   forward : in  a[n1] = x[RX n1 + t]      out a[k2] = X[t + RX k2]
+//   inverse : in  a[k2] = X[t + RX k2]      out a[n1] = x[RX n1 + t]      (unnormalised)
+// `grp` is the lane mask of the RX cooperating threads (the only ones that synchronise).
+__device__ __forceinline__ unsigned line_group_mask(int rx) {
+  const int lane = threadIdx.x & 31;
+  return (rx == 32 ? 0xffffffffu : ((1u << rx) - 1u)) << (lane & ~(rx - 1));
+}
+template <int RX>
+__device__ __forceinline__ void line_fft_forward(float2 (&a)[RX], float2* x, const float2* tw, int t, unsigned grp) {
+  fft_reg<RX, -1>(a);  // over n1 -> k1
+#pragma unroll
+  for (int k1 = 0; k1 < RX; ++k1) x[t * (RX + 1) + k1] = cmul(a[k1], tw[t * k1]);
+  __syncwarp(grp);
+#pragma unroll
+  for (int n2 = 0; n2 < RX; ++n2) a[n2] = x[n2 * (RX + 1) + t];
+  fft_reg<RX, -1>(a);  // over n2 -> k2
+}
+template <int RX>
+__device__ __forceinline__ void line_fft_inverse(float2 (&a)[RX], float2* x, const float2* tw, int t, unsigned grp) {
+  fft_reg<RX, 1>(a);  // over k2 -> n2
+#pragma unroll
+  for (int n2 = 0; n2 < RX; ++n2) {
+    float2 w = tw[t * n2];
+    w.y = -w.y;
+    x[n2 * (RX + 1) + t] = cmul(a[n2], w);
+  }
+  __syncwarp(grp);
+#pragma unroll
+  for (int k1 = 0; k1 < RX; ++k1) a[k1] = x[t * (RX + 1) + k1];
+  fft_reg<RX, 1>(a);  // over k1 -> n1
+}
+
+template <int RX, int RB>
+struct FusedGeom {
+  static constexpr int N = RX * RX;
+  static constexpr int kSlabRows = RB + 5;        // rows i0-3 .. i0+RB+1
+  static constexpr int kLine = RX * (RX + 1);     // float2 per line buffer
+  static constexpr int kWarps = N / 32;
+  static constexpr size_t slab_bytes = (size_t)2 * kSlabRows * N * sizeof(float);
+  static constexpr size_t line_bytes = (size_t)RB * kLine * sizeof(float2);
+  static constexpr size_t misc_bytes = (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) +
+                                       (size_t)2 * kWarps * (RB + 1) * sizeof(float) + (size_t)kWarps * RB * sizeof(float);
+  static constexpr size_t smem_a = slab_bytes + line_bytes + misc_bytes;
+  static constexpr int kThreadsC = ((RX * (RB + 1) > N ? RX * (RB + 1) : N) + 31) / 32 * 32;
+  static constexpr size_t smem_c = (size_t)(RB + 1) * kLine * sizeof(float2) + (size_t)N * sizeof(float2);
+};
+
+// grid: (N / RB, npairs), block: N threads (one per column).
+template <int RX, int RB>
+__global__ void __launch_bounds__(RX* RX)
+    fused_explicit_rowfft_kernel(const float* __restrict__ uv, float* __restrict__ uvs, float2* __restrict__ spec,
+                                 int E, float dt, float h, float nu) {
+  using G = FusedGeom<RX, RB>;
+  constexpr int N = G::N, mask = N - 1, SR = G::kSlabRows, LS = G::kLine, NW = G::kWarps;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  float* su = reinterpret_cast<float*>(fsm);           // [SR][N]
+  float* sv = su + SR * N;                             // [SR][N]
+  float2* zl = reinterpret_cast<float2*>(sv + SR * N);  // [RB][LS]
+  float2* tw = zl + RB * LS;                           // [N]
+  float* sforce = reinterpret_cast<float*>(tw + N);    // [N]
+  float* fyb = sforce + N;                             // [2][NW][RB + 1]
+  float* vsb = fyb + 2 * NW * (RB + 1);                // [NW][RB]
+
+  const int tid = threadIdx.x, j = tid, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * RB, pair = blockIdx.y;
+  const float dt_h = dt / h, inv_h = 1.f / h, inv_h2 = 1.f / (h * h);
+
+  fill_twiddles_full(tw, N, tid, N);
+  sforce[j] = sinf(4.f * ((float)j + 0.5f) * h);  // Kolmogorov forcing at u's offset y_{j+1/2}
+
+#define U(k, dj) su[((k) + 3) * N + ((j + (dj)) & mask)]
+#define V(k, dj) sv[((k) + 3) * N + ((j + (dj)) & mask)]
+  for (int m = 0; m < 2; ++m) {
+    const int e = 2 * pair + m;
+    if (e >= E) {  // odd ensemble: the missing partner contributes a zero field
+      __syncthreads();
+      for (int idx = tid; idx < RB * N; idx += N) zl[(idx / N) * LS + (idx % N)].y = 0.f;
+      break;
+    }
+    const float* u = uv + (size_t)e * 2 * N * N;
+    const float* v = u + (size_t)N * N;
+    __syncthreads();  // previous member's march has finished reading the slab
+    for (int idx = tid; idx < SR * (N / 4); idx += N) {
+      const int li = idx / (N / 4), c4 = idx % (N / 4);
+      const int gi = (i0 - 3 + li) & mask;
+      reinterpret_cast<float4*>(su)[idx] = reinterpret_cast<const float4*>(u + (size_t)gi * N)[c4];
+      reinterpret_cast<float4*>(sv)[idx] = reinterpret_cast<const float4*>(v + (size_t)gi * N)[c4];
+    }
+    __syncthreads();
+    // y-face fluxes through the right face of the column left of every warp (lane 0's left face)
+    if (tid < NW * (RB + 1)) {
+      const int w = tid / (RB + 1), k = tid % (RB + 1) - 1;
+      const int jb = (32 * w - 1) & mask;
+#define UB(kk, dj) su[((kk) + 3) * N + ((jb + (dj)) & mask)]
+#define VB(kk, dj) sv[((kk) + 3) * N + ((jb + (dj)) & mask)]
+      const float vfu = 0.5f * (VB(k, 0) + VB(k + 1, 0));
+      fyb[w * (RB + 1) + k + 1] = face_value(UB(k, -1), UB(k, 0), UB(k, 1), UB(k, 2), vfu, dt_h) * vfu;
+      const float vfv = 0.5f * (VB(k, 0) + VB(k, 1));
+      fyb[(NW + w) * (RB + 1) + k + 1] = face_value(VB(k, -1), VB(k, 0), VB(k, 1), VB(k, 2), vfv, dt_h) * vfv;
+#undef UB
+#undef VB
+    }
+    __syncthreads();
+    // march down the column: the flux through the lower x face of a cell is the upper-face flux
+    // of the previous row (register), the left y-face flux comes from the neighbouring lane
+    float* us = uvs + (size_t)e * 2 * N * N;
+    float* vs = us + (size_t)N * N;
+    float fxu_prev = 0.f, fxv_prev = 0.f, ustar_prev = 0.f;
+#pragma unroll 1
+    for (int k = -2; k < RB; ++k) {
+      const float u00 = U(k, 0), v00 = V(k, 0);
+      const float ufu = 0.5f * (u00 + U(k + 1, 0));
+      const float fxu = face_value(U(k - 1, 0), u00, U(k + 1, 0), U(k + 2, 0), ufu, dt_h) * ufu;
+      const float ufv = 0.5f * (u00 + U(k, 1));
+      const float fxv = face_value(V(k - 1, 0), v00, V(k + 1, 0), V(k + 2, 0), ufv, dt_h) * ufv;
+      if (k >= -1) {
+        const float vfu = 0.5f * (v00 + V(k + 1, 0));
+        const float fyu = face_value(U(k, -1), u00, U(k, 1), U(k, 2), vfu, dt_h) * vfu;
+        const float vfv = 0.5f * (v00 + V(k, 1));
+        const float fyv = face_value(V(k, -1), v00, V(k, 1), V(k, 2), vfv, dt_h) * vfv;
+        float fyu_m = __shfl_up_sync(0xffffffffu, fyu, 1), fyv_m = __shfl_up_sync(0xffffffffu, fyv, 1);
+        if (lane == 0) fyu_m = fyb[warp * (RB + 1) + k + 1], fyv_m = fyb[(NW + warp) * (RB + 1) + k + 1];
+        const float conv_u = -((fxu - fxu_prev) + (fyu - fyu_m)) * inv_h;
+        const float lap_u = (U(k + 1, 0) + U(k - 1, 0) + U(k, 1) + U(k, -1) - 4.f * u00) * inv_h2;
+        const float ustar = u00 + dt * (conv_u + nu * lap_u + (sforce[j] - 0.1f * u00));
+        const float conv_v = -((fxv - fxv_prev) + (fyv - fyv_m)) * inv_h;
+        const float lap_v = (V(k + 1, 0) + V(k - 1, 0) + V(k, 1) + V(k, -1) - 4.f * v00) * inv_h2;
+        const float vstar = v00 + dt * (conv_v + nu * lap_v - 0.1f * v00);
+        const float vleft = __shfl_up_sync(0xffffffffu, vstar, 1);
+        if (k >= 0) {
+          const int gi = i0 + k;
+          us[(size_t)gi * N + j] = ustar;
+          vs[(size_t)gi * N + j] = vstar;
+          // backward-difference divergence; lane 0 lacks v*(j-1), fixed up below from vsb
+          const float zp = ((ustar - ustar_prev) + (lane ? vstar - vleft : vstar)) * inv_h;
+          float* zc = reinterpret_cast<float*>(zl + k * LS + j) + m;
+          *zc = zp;
+          if (lane == 31) vsb[warp * RB + k] = vstar;
+        }
+        ustar_prev = ustar;
+      }
+      fxu_prev = fxu, fxv_prev = fxv;
+    }
+    __syncthreads();
+    if (tid < NW * RB) {
+      const int w = tid / RB, k = tid % RB;
+      float* zc = reinterpret_cast<float*>(zl + k * LS + 32 * w) + m;
+      *zc -= vsb[((w + NW - 1) % NW) * RB + k] * inv_h;
+    }
+  }
+#undef U
+#undef V
+  __syncthreads();
+  // FFT along y of the RB lines, RX threads per line
+  for (int line = tid / RX; line < RB; line += N / RX) {
+    const int t = tid % RX;
+    float2* x = zl + line * LS;
+    float2 a[RX];
+#pragma unroll
+    for (int n1 = 0; n1 < RX; ++n1) a[n1] = x[RX * n1 + t];
+    const unsigned grp = line_group_mask(RX);
+    __syncwarp(grp);
+    line_fft_forward<RX>(a, x, tw, t, grp);
+    float2* dst = spec + ((size_t)pair * N + (i0 + line)) * N;
+#pragma unroll
+    for (int k2 = 0; k2 < RX; ++k2) dst[t + RX * k2] = a[k2];
+  }
+}
+
+// FFT along x, multiply by 1 / (lambda_x + lambda_y) / N^2 (zero mode -> 0), inverse FFT along x.
+// grid: (N / 16, npairs), block: 16 columns x RX threads; thread (r, c) = tid / 16, tid % 16.
+template <int RX>
+__global__ void __launch_bounds__(16 * RX) fused_col_solve_kernel(float2* __restrict__ spec, float h) {
+  constexpr int N = RX * RX, LC = RX * (RX + 1) + 1;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  float2* xch = reinterpret_cast<float2*>(fsm);  // [16][LC]
+  float2* tw = xch + 16 * LC;                    // [N]
+  float* lam = reinterpret_cast<float*>(tw + N);  // [N]
+  const int tid = threadIdx.x, c = tid & 15, r = tid >> 4;
+  fill_twiddles_full(tw, N, tid, 16 * RX);
+  for (int k = tid; k < N; k += 16 * RX) {
+    const float s = sinpif((float)k / (float)N);
+    lam[k] = -4.f * s * s / (h * h);
+  }
+  const int py = blockIdx.x * 16 + c;  // y frequency of this column (natural order)
+  float2* base = spec + (size_t)blockIdx.y * N * N + py;
+  float2* x = xch + c * LC;
+  float2 a[RX];
+#pragma unroll
+  for (int n1 = 0; n1 < RX; ++n1) a[n1] = base[(size_t)(RX * n1 + r) * N];
+  __syncthreads();
+  fft_reg<RX, -1>(a);
+#pragma unroll
+  for (int k1 = 0; k1 < RX; ++k1) x[r * (RX + 1) + k1] = cmul(a[k1], tw[r * k1]);
+  __syncthreads();
+#pragma unroll
+  for (int n2 = 0; n2 < RX; ++n2) a[n2] = x[n2 * (RX + 1) + r];
+  fft_reg<RX, -1>(a);  // a[k2] = X[kx = r + RX k2]
+  const float scale = 1.f / ((float)N * (float)N);
+  const float ly = lam[py];
+#pragma unroll
+  for (int k2 = 0; k2 < RX; ++k2) {
+    const int kx = r + RX * k2;
+    const float f = (kx | py) ? __fdividef(scale, lam[kx] + ly) : 0.f;
+    a[k2].x *= f, a[k2].y *= f;
+  }
+  fft_reg<RX, 1>(a);  // over k2 -> n2
+#pragma unroll
+  for (int n2 = 0; n2 < RX; ++n2) {
+    float2 w = tw[r * n2];
+    w.y = -w.y;
+    x[n2 * (RX + 1) + r] = cmul(a[n2], w);  // the slots this thread read above
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k1 = 0; k1 < RX; ++k1) a[k1] = x[r * (RX + 1) + k1];
+  fft_reg<RX, 1>(a);
+#pragma unroll
+  for (int n1 = 0; n1 < RX; ++n1) base[(size_t)(RX * n1 + r) * N] = a[n1];
+}
+
+// inverse FFT along y of rows i0 .. i0 + RB (one extra row for the x difference), then
+// v = v* - grad q (forward differences).  grid: (N / RB, npairs), block: kThreadsC.
+template <int RX, int RB>
+__global__ void __launch_bounds__(FusedGeom<RX, RB>::kThreadsC)
+    fused_rowifft_grad_kernel(const float2* __restrict__ spec, const float* __restrict__ uvs, float* __restrict__ uv,
+                              int E, float h) {
+  using G = FusedGeom<RX, RB>;
+  constexpr int N = G::N, mask = N - 1, LS = G::kLine;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  float2* ql = reinterpret_cast<float2*>(fsm);  // [RB + 1][LS]
+  float2* tw = ql + (RB + 1) * LS;              // [N]
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * RB, pair = blockIdx.y;
+  fill_twiddles_full(tw, N, tid, blockDim.x);
+  __syncthreads();
+  for (int line = tid / RX; line <= RB; line += blockDim.x / RX) {
+    const int t = tid % RX;
+    const float2* src = spec + ((size_t)pair * N + ((i0 + line) & mask)) * N;
+    float2* x = ql + line * LS;
+    float2 a[RX];
+#pragma unroll
+    for (int k2 = 0; k2 < RX; ++k2) a[k2] = src[t + RX * k2];
+    const unsigned grp = line_group_mask(RX);
+    line_fft_inverse<RX>(a, x, tw, t, grp);
+    __syncwarp(grp);
+#pragma unroll
+    for (int n1 = 0; n1 < RX; ++n1) x[RX * n1 + t] = a[n1];
+  }
+  __syncthreads();
+  // thread = 4 consecutive columns of one row group
+  constexpr int kColGroups = N / 4, kRowGroups = (N >= 256 ? 256 : N) / kColGroups;
+  if (tid >= kColGroups * kRowGroups) return;
+  const int cg = tid % kColGroups, rg = tid / kColGroups;
+  const float inv_h = 1.f / h;
+  for (int k = rg; k < RB; k += kRowGroups) {
+    const int gi = i0 + k;
+    float2 q0[5], q1[4];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) q0[d] = ql[k * LS + ((4 * cg + d) & mask)];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) q1[d] = ql[(k + 1) * LS + 4 * cg + d];
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int e = 2 * pair + m;
+      if (e >= E) break;
+      const size_t o = (size_t)e * 2 * N * N + (size_t)gi * N + 4 * cg;
+      float4 us = *reinterpret_cast<const float4*>(uvs + o);
+      float4 vs = *reinterpret_cast<const float4*>(uvs + o + (size_t)N * N);
+#define Q(arr, d) (m ? arr[d].y : arr[d].x)
+      us.x -= (Q(q1, 0) - Q(q0, 0)) * inv_h, us.y -= (Q(q1, 1) - Q(q0, 1)) * inv_h;
+      us.z -= (Q(q1, 2) - Q(q0, 2)) * inv_h, us.w -= (Q(q1, 3) - Q(q0, 3)) * inv_h;
+      vs.x -= (Q(q0, 1) - Q(q0, 0)) * inv_h, vs.y -= (Q(q0, 2) - Q(q0, 1)) * inv_h;
+      vs.z -= (Q(q0, 3) - Q(q0, 2)) * inv_h, vs.w -= (Q(q0, 4) - Q(q0, 3)) * inv_h;
+#undef Q
+      *reinterpret_cast<float4*>(uv + o) = us;
+      *reinterpret_cast<float4*>(uv + o + (size_t)N * N) = vs;
+    }
+  }
+}
+
 }  // namespace
 
 }  // namespace sdab
@@ -354,6 +714,71 @@ int project(const sdab_kolmogorov* k, const float* src, float* dst, float2* spec
   return SDAB_OK;
 }
 
+// ---------------------------------------------------------------------------- fast path (host)
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+bool fast_path(int N) {
+  static const int on = env_int("SDAB_KOLMO_FAST", 1);
+  return on && (N == 64 || N == 256);
+}
+
+template <int RX, int RB>
+int inner_step_fast(const sdab_kolmogorov* k, float* uv, float* uvs, float2* spec, int E, cudaStream_t st) {
+  using G = FusedGeom<RX, RB>;
+  constexpr int N = G::N;
+  const int npairs = (E + 1) / 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(fused_explicit_rowfft_kernel<RX, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G::smem_a));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(fused_rowifft_grad_kernel<RX, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G::smem_c));
+    attr_set = true;
+  }
+  fused_explicit_rowfft_kernel<RX, RB><<<dim3(N / RB, npairs), N, G::smem_a, st>>>(uv, uvs, spec, E, k->dt_inner, k->h, k->nu);
+  SDAB_LAUNCH_CHECK("fused_explicit_rowfft_kernel");
+  constexpr size_t smem_b = (size_t)16 * (RX * (RX + 1) + 1) * sizeof(float2) + (size_t)N * sizeof(float2) + (size_t)N * sizeof(float);
+  fused_col_solve_kernel<RX><<<dim3(N / 16, npairs), 16 * RX, smem_b, st>>>(spec, k->h);
+  SDAB_LAUNCH_CHECK("fused_col_solve_kernel");
+  fused_rowifft_grad_kernel<RX, RB><<<dim3(N / RB, npairs), G::kThreadsC, G::smem_c, st>>>(spec, uvs, uv, E, k->h);
+  SDAB_LAUNCH_CHECK("fused_rowifft_grad_kernel");
+  return SDAB_OK;
+}
+
+// The ensemble is walked in chunks of (an even number of) members whose working set -- state,
+// u*/v* and the pair spectra, 20 N^2 bytes per member -- stays resident in the 126 MB L2 for all
+// inner steps of all transitions; members are independent, so the order does not change results.
+int transition_fast(const sdab_kolmogorov* k, float* uv, int E, int n_transitions, float* traj, const KWs& w,
+                    cudaStream_t st) {
+  const int N = k->N;
+  const size_t n2 = (size_t)N * N, state = (size_t)E * 2 * n2;
+  static const int chunk_mb = env_int("SDAB_KOLMO_L2_MB", 88);
+  static const int rb256 = env_int("SDAB_KOLMO_RB", 16);
+  int chunk = (int)((size_t)chunk_mb * 1024 * 1024 / (20 * n2));
+  chunk = chunk < 2 ? 2 : chunk & ~1;
+  for (int e0 = 0; e0 < E; e0 += chunk) {
+    const int ne = E - e0 < chunk ? E - e0 : chunk;
+    float* cuv = uv + (size_t)e0 * 2 * n2;
+    float* cuvs = w.uvs + (size_t)e0 * 2 * n2;
+    float2* cspec = w.spec + (size_t)(e0 / 2) * n2;
+    for (int t = 0; t < n_transitions; ++t) {
+      for (int s = 0; s < k->steps; ++s) {
+        if (N == 64)
+          SDAB_TRY((inner_step_fast<8, 8>(k, cuv, cuvs, cspec, ne, st)));
+        else if (rb256 == 8)
+          SDAB_TRY((inner_step_fast<16, 8>(k, cuv, cuvs, cspec, ne, st)));
+        else
+          SDAB_TRY((inner_step_fast<16, 16>(k, cuv, cuvs, cspec, ne, st)));
+      }
+      if (traj) SDAB_TRY(copy_f32(cuv, traj + (size_t)t * state + (size_t)e0 * 2 * n2, (size_t)ne * 2 * n2, st));
+    }
+  }
+  return SDAB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -396,6 +821,7 @@ int sdab_kolmogorov_transition(sdab_kolmogorov* k, float* uv, int E, int n_trans
   cudaStream_t st = (cudaStream_t)stream;
   const int N = k->N;
   const size_t state = (size_t)E * 2 * N * N;
+  if (fast_path(N)) return transition_fast(k, uv, E, n_transitions, traj, w, st);
   for (int t = 0; t < n_transitions; ++t) {
     for (int s = 0; s < k->steps; ++s) {
       explicit_step_kernel<<<dim3(N / kTile, N / kTile, E), dim3(32, 8), 0, st>>>(uv, w.uvs, N, k->dt_inner, k->h,
