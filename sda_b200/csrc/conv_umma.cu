@@ -38,6 +38,17 @@ constexpr uint32_t kStageO = 128 * 64;       // 128 pixels x 32 bf16 channels (S
 constexpr uint32_t kStagingBytes = kStageF + 2 * kStageO;
 constexpr uint32_t kSmemBudget = 227 * 1024;
 constexpr int kMaxStages = 8;
+// Patch kernel: the M tile is 8 x 16 pixels of one image, its haloed 10 x 18 input patch is ONE TMA box
+// per (plane, K-block), and tap (a, b) is the same shared-memory tile addressed through a descriptor
+// whose start is shifted by (10 a + b) pixel rows (64 B each) with a stride-byte-offset of one patch
+// row (640 B).  SWIZZLE_64B is a function of the shared-memory address bits alone, so shifted
+// starts need no base-offset correction (verified on hardware by tools/probes/umma_shift_probe.cu).
+constexpr int kPatchBW = 8, kPatchBH = 16;
+constexpr int kPatchW = kPatchBW + 2, kPatchH = kPatchBH + 2;
+constexpr uint32_t kPatchBytes = kPatchW * kPatchH * 64;  // 11520 B landing per (plane, K-block)
+constexpr uint32_t kPatchPlane = 12288;                   // padded to the 1 KB swizzle alignment
+constexpr uint32_t kPatchSBO = kPatchW * 64;
+constexpr int kMaxBStages = 16, kMaxAStages = 4;
 
 struct UmmaParams {
   TileGeom g;
@@ -53,6 +64,9 @@ struct UmmaParams {
   int staged;      // epilogue through shared memory + TMA stores (C_out % 32 == 0)
   int sbufs;       // number of staging sets (TMA stores in flight behind the epilogue)
   int out_chunks;  // C_out / 32
+  int patch;       // patch kernel: one haloed input patch per K-block serves all nine taps
+  int a_stages;    // patch kernel: depth of the patch ring (`stages` is the depth of the weight ring)
+  uint32_t b_stage_bytes;
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
@@ -302,6 +316,239 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
          ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 
+// ------------------------------------------------------------------------------------------ epilogue
+// Epilogue role (warps 2..5 of both kernels): TMEM -> registers -> fused bias / residual / activation /
+// activation-derivative / LayerNorm (forward or adjoint) / bf16 split -> staged TMA stores.
+template <int LN, bool CTA2>
+__device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
+                                              uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
+                                              uint32_t acc_stride, uint32_t staging0, int tile_begin, int tile_end,
+                                              int warp, int lane) {
+  const int q = warp & 3;  // TMEM lane quarter accessible to this warp
+  const int m = q * 32 + lane;
+  const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
+  int it = 0;
+  int sbuf = 0;  // staging set of the next 32-channel block (running over tiles)
+  for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
+    const int acc = it % p.acc_stages;
+    const uint32_t acc_phase = (it / p.acc_stages) & 1;
+    int n0, h0, w0;
+    p.g.tile_origin(tile, n0, h0, w0);
+    // (h, w): output pixel of this thread in the (Ho x Wo) output image (ConvProblem::os, oh0, ow0)
+    const int n = n0 + bn, h = p.os * (h0 + bh) + p.oh0, w = p.os * (w0 + bw) + p.ow0;
+    const bool valid = n < p.N;
+    const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+    mbar_wait(bar_tfull + 8 * acc, acc_phase);
+    tc_fence_after();
+    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
+    if (p.debug & 4) {
+      // ablation: no epilogue work
+    } else if (!p.staged) {
+      for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+        float v[16];
+        tmem_ld16(t0 + c0, v);
+        if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.Ho, p.Wo, p.Cout, c0);
+      }
+    } else {
+      // Staged epilogue: every output leaves the SM as full cache lines.  Per 32-channel block the
+      // 128 threads (one pixel each) write their values into swizzled staging tiles; one thread
+      // then issues TMA stores (F: [pixels][C] matrix, OP: the (plane, K-block) image box).
+      const bool wantF = p.epi.outF != nullptr || p.epi.pre != nullptr;
+      const bool wantO = p.epi.outOP != nullptr;
+      const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
+      const OpShape so{0, p.Ho, p.Wo, p.Cout, 0};
+      constexpr int ln = LN;  // fused LayerNorm variant (ConvEpilogue::ln), compile-time to keep registers down
+      // developer ablation bits: 8 = no LayerNorm statistics pass, 16 = no global operand loads, 32 = no stores
+      const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
+      {
+        // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
+        const int nt = tile + gridDim.x;
+        if (nt < p.g.num_tiles) {
+          int nn0, nh0, nw0;
+          p.g.tile_origin(nt, nn0, nh0, nw0);
+          const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
+          if (nn < p.N) {
+            const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
+            const float* pf = p.epi.res ? p.epi.res : p.epi.dact;
+            if (pf)
+              for (int c = 0; c < p.Cout; c += 32) prefetch_l2(pf + npix * p.Cout + c);
+            if (ln == 2) {
+              const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
+              for (int c = 0; c < 2 * p.out_chunks; ++c) prefetch_l2(pa + (size_t)c * so.block_stride());
+            }
+          }
+        }
+      }
+      const float invC = 1.f / (float)p.Cout, invC1 = 1.f / (float)(p.Cout - 1);
+      // fused LayerNorm statistics (first pass over the accumulator)
+      float st_a = 0.f, st_b = 0.f, st_r = 1.f;  // forward: mean, -, rstd ; backward: mean(g), sum(g a)/(C-1), rstd
+      const float* shiftp =
+          (ln == 1 && p.epi.ln_shift) ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride
+                                      : nullptr;
+      const bf16* a_pix = (ln == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
+      if (ln == 1 && !(p.debug & 8)) {
+        float s1 = 0.f, s2 = 0.f, K = 0.f;
+        for (int cc = 0; cc < p.out_chunks; ++cc) {
+          float v[32], f[32], rr[32];
+          if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
+          tmem_ld32(t0 + cc * 32, v);
+          epilogue_math32(p.epi, v, f, rr, has_res, false, cc * 32);
+          if (shiftp) {
+            float sh[32];
+            load32_ldg(shiftp + cc * 32, sh);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += sh[j];
+          }
+          if (cc == 0) K = f[0];  // shifted one-pass variance: accumulate around the first channel
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float u = f[j] - K;
+            s1 += u;
+            s2 += u * u;
+          }
+        }
+        st_a = K + s1 * invC;
+        const float var = fmaxf(s2 - s1 * s1 * invC, 0.f) * invC1;
+        st_r = 1.f / sqrtf(var + 1e-5f);
+        if (valid && p.epi.ln_rstd_out) p.epi.ln_rstd_out[pix] = st_r;
+      } else if (ln == 2 && !(p.debug & 8)) {
+        float sg = 0.f, sga = 0.f;
+        for (int cc = 0; cc < p.out_chunks; ++cc) {
+          float g[32], a[32];
+          if (valid) {
+            const bf16* ah = a_pix + (size_t)cc * so.block_stride();
+            load32_hilo(ah, ah + so.lo_offset(), a);
+          }
+          tmem_ld32(t0 + cc * 32, g);
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              sg += g[j];
+              sga += g[j] * a[j];
+            }
+          }
+        }
+        st_a = sg * invC, st_b = sga * invC1;
+        st_r = valid ? p.epi.ln_rstd_in[pix] : 1.f;
+      }
+      for (int cc = 0; cc < p.out_chunks; ++cc) {
+        float v[32], f[32], rr[32], aa[32];
+        // operands from global memory first: their latency overlaps the accumulator load
+        if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
+        if (has_dact) load32(p.epi.dact + pix * p.Cout + cc * 32, rr);
+        if (ln == 2 && valid && !(p.debug & 16)) {
+          const bf16* ah = a_pix + (size_t)cc * so.block_stride();
+          load32_hilo(ah, ah + so.lo_offset(), aa);
+        }
+        tmem_ld32(t0 + cc * 32, v);
+        if (cc == p.out_chunks - 1) {
+          // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (CTA2)
+              mbar_arrive_leader(bar_tempty + 8 * acc);
+            else
+              mbar_arrive(bar_tempty + 8 * acc);
+          }
+        }
+        if (ln == 2) {
+          // backward of the LayerNorm: gx = res + (g - mean g - a sum(g a)/(C-1)) rstd
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (v[j] - st_a - aa[j] * st_b) * st_r + (has_res ? rr[j] : 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = v[j];
+        } else {
+          epilogue_math32(p.epi, v, f, rr, has_res, has_dact, cc * 32);
+          if (ln == 1) {
+            float sh[32];
+            if (shiftp) load32_ldg(shiftp + cc * 32, sh);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (f[j] + (shiftp ? sh[j] : 0.f) - st_a) * st_r;
+          }
+        }
+        if (p.debug & 32) continue;
+        // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
+        const uint32_t staging = staging0 + sbuf * kStagingBytes;
+        if (threadIdx.x == 64) {
+          if (p.sbufs == 1)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          else if (p.sbufs == 2)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else
+            asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+        }
+        EPI_BARRIER();
+        if (wantF) {
+          const uint32_t row = staging + m * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            st_shared_v4(row + ((j ^ (m & 7)) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                         __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+        }
+        if (wantO) {
+          __align__(16) bf16 hi[32];
+          __align__(16) bf16 lo[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) split_bf16(v[j], hi[j], lo[j]);
+          const uint32_t rh = staging + kStageF + m * 64, rl = rh + kStageO;
+          const uint32_t* ph = reinterpret_cast<const uint32_t*>(hi);
+          const uint32_t* pl = reinterpret_cast<const uint32_t*>(lo);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t sw = (j ^ ((m >> 1) & 3)) << 4;
+            st_shared_v4(rh + sw, ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+            st_shared_v4(rl + sw, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+          }
+          if (edge) {
+            // halo replicas of edge pixels (the TMA box covers the interior position only)
+            const size_t blk = (size_t)cc * so.block_stride(), lo_off = so.lo_offset();
+            bool first = true;
+            for_each_replica(h, w, p.Ho, p.Wo, [&](int hp, int wp) {
+              if (first) {
+                first = false;
+                return;
+              }
+              bf16* dst = p.epi.outOP + op_offset(so, n, hp, wp) + blk;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(hi)[j];
+                reinterpret_cast<uint4*>(dst + lo_off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+              }
+            });
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        EPI_BARRIER();
+        if (threadIdx.x == 64 && !(p.debug & 128)) {
+          // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
+          // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
+          // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
+          if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
+          if (wantO) {
+            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
+            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + cc, n0);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        if (++sbuf == p.sbufs) sbuf = 0;
+      }
+      continue;  // tempty already signalled
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (CTA2)
+        mbar_arrive_leader(bar_tempty + 8 * acc);
+      else
+        mbar_arrive(bar_tempty + 8 * acc);
+    }
+  }
+  if (p.staged && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 // One lane of the (converged) warp; the compiler keeps the guarded block on the uniform datapath.
 __device__ __forceinline__ bool elect_one() {
@@ -498,229 +745,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter accessible to this warp
-    const int m = q * 32 + lane;
-    const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
-    int it = 0;
-    int sbuf = 0;  // staging set of the next 32-channel block (running over tiles)
-    for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
-      const int acc = it % p.acc_stages;
-      const uint32_t acc_phase = (it / p.acc_stages) & 1;
-      int n0, h0, w0;
-      p.g.tile_origin(tile, n0, h0, w0);
-      // (h, w): output pixel of this thread in the (Ho x Wo) output image (ConvProblem::os, oh0, ow0)
-      const int n = n0 + bn, h = p.os * (h0 + bh) + p.oh0, w = p.os * (w0 + bw) + p.ow0;
-      const bool valid = n < p.N;
-      const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
-      if (p.debug & 4) {
-        // ablation: no epilogue work
-      } else if (!p.staged) {
-        for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-          float v[16];
-          tmem_ld16(t0 + c0, v);
-          if (valid) epilogue_store16(p.epi, v, pix, n, h, w, p.Ho, p.Wo, p.Cout, c0);
-        }
-      } else {
-        // Staged epilogue: every output leaves the SM as full cache lines.  Per 32-channel block the
-        // 128 threads (one pixel each) write their values into swizzled staging tiles; one thread
-        // then issues TMA stores (F: [pixels][C] matrix, OP: the (plane, K-block) image box).
-        const bool wantF = p.epi.outF != nullptr || p.epi.pre != nullptr;
-        const bool wantO = p.epi.outOP != nullptr;
-        const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
-        const OpShape so{0, p.Ho, p.Wo, p.Cout, 0};
-        constexpr int ln = LN;  // fused LayerNorm variant (ConvEpilogue::ln), compile-time to keep registers down
-        // developer ablation bits: 8 = no LayerNorm statistics pass, 16 = no global operand loads, 32 = no stores
-        const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
-        {
-          // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
-          const int nt = tile + gridDim.x;
-          if (nt < p.g.num_tiles) {
-            int nn0, nh0, nw0;
-            p.g.tile_origin(nt, nn0, nh0, nw0);
-            const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
-            if (nn < p.N) {
-              const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
-              const float* pf = p.epi.res ? p.epi.res : p.epi.dact;
-              if (pf)
-                for (int c = 0; c < p.Cout; c += 32) prefetch_l2(pf + npix * p.Cout + c);
-              if (ln == 2) {
-                const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
-                for (int c = 0; c < 2 * p.out_chunks; ++c) prefetch_l2(pa + (size_t)c * so.block_stride());
-              }
-            }
-          }
-        }
-        const float invC = 1.f / (float)p.Cout, invC1 = 1.f / (float)(p.Cout - 1);
-        // fused LayerNorm statistics (first pass over the accumulator)
-        float st_a = 0.f, st_b = 0.f, st_r = 1.f;  // forward: mean, -, rstd ; backward: mean(g), sum(g a)/(C-1), rstd
-        const float* shiftp =
-            (ln == 1 && p.epi.ln_shift) ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride
-                                        : nullptr;
-        const bf16* a_pix = (ln == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
-        if (ln == 1 && !(p.debug & 8)) {
-          float s1 = 0.f, s2 = 0.f, K = 0.f;
-          for (int cc = 0; cc < p.out_chunks; ++cc) {
-            float v[32], f[32], rr[32];
-            if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
-            tmem_ld32(t0 + cc * 32, v);
-            epilogue_math32(p.epi, v, f, rr, has_res, false, cc * 32);
-            if (shiftp) {
-              float sh[32];
-              load32_ldg(shiftp + cc * 32, sh);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += sh[j];
-            }
-            if (cc == 0) K = f[0];  // shifted one-pass variance: accumulate around the first channel
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float u = f[j] - K;
-              s1 += u;
-              s2 += u * u;
-            }
-          }
-          st_a = K + s1 * invC;
-          const float var = fmaxf(s2 - s1 * s1 * invC, 0.f) * invC1;
-          st_r = 1.f / sqrtf(var + 1e-5f);
-          if (valid && p.epi.ln_rstd_out) p.epi.ln_rstd_out[pix] = st_r;
-        } else if (ln == 2 && !(p.debug & 8)) {
-          float sg = 0.f, sga = 0.f;
-          for (int cc = 0; cc < p.out_chunks; ++cc) {
-            float g[32], a[32];
-            if (valid) {
-              const bf16* ah = a_pix + (size_t)cc * so.block_stride();
-              load32_hilo(ah, ah + so.lo_offset(), a);
-            }
-            tmem_ld32(t0 + cc * 32, g);
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                sg += g[j];
-                sga += g[j] * a[j];
-              }
-            }
-          }
-          st_a = sg * invC, st_b = sga * invC1;
-          st_r = valid ? p.epi.ln_rstd_in[pix] : 1.f;
-        }
-        for (int cc = 0; cc < p.out_chunks; ++cc) {
-          float v[32], f[32], rr[32], aa[32];
-          // operands from global memory first: their latency overlaps the accumulator load
-          if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
-          if (has_dact) load32(p.epi.dact + pix * p.Cout + cc * 32, rr);
-          if (ln == 2 && valid && !(p.debug & 16)) {
-            const bf16* ah = a_pix + (size_t)cc * so.block_stride();
-            load32_hilo(ah, ah + so.lo_offset(), aa);
-          }
-          tmem_ld32(t0 + cc * 32, v);
-          if (cc == p.out_chunks - 1) {
-            // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if constexpr (CTA2)
-                mbar_arrive_leader(bar_tempty + 8 * acc);
-              else
-                mbar_arrive(bar_tempty + 8 * acc);
-            }
-          }
-          if (ln == 2) {
-            // backward of the LayerNorm: gx = res + (g - mean g - a sum(g a)/(C-1)) rstd
-            if (valid) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (v[j] - st_a - aa[j] * st_b) * st_r + (has_res ? rr[j] : 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = v[j];
-          } else {
-            epilogue_math32(p.epi, v, f, rr, has_res, has_dact, cc * 32);
-            if (ln == 1) {
-              float sh[32];
-              if (shiftp) load32_ldg(shiftp + cc * 32, sh);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = (f[j] + (shiftp ? sh[j] : 0.f) - st_a) * st_r;
-            }
-          }
-          if (p.debug & 32) continue;
-          // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
-          const uint32_t staging = staging0 + sbuf * kStagingBytes;
-          if (threadIdx.x == 64) {
-            if (p.sbufs == 1)
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            else if (p.sbufs == 2)
-              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            else
-              asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-          }
-          EPI_BARRIER();
-          if (wantF) {
-            const uint32_t row = staging + m * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              st_shared_v4(row + ((j ^ (m & 7)) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
-                           __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
-          }
-          if (wantO) {
-            __align__(16) bf16 hi[32];
-            __align__(16) bf16 lo[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) split_bf16(v[j], hi[j], lo[j]);
-            const uint32_t rh = staging + kStageF + m * 64, rl = rh + kStageO;
-            const uint32_t* ph = reinterpret_cast<const uint32_t*>(hi);
-            const uint32_t* pl = reinterpret_cast<const uint32_t*>(lo);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t sw = (j ^ ((m >> 1) & 3)) << 4;
-              st_shared_v4(rh + sw, ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-              st_shared_v4(rl + sw, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-            }
-            if (edge) {
-              // halo replicas of edge pixels (the TMA box covers the interior position only)
-              const size_t blk = (size_t)cc * so.block_stride(), lo_off = so.lo_offset();
-              bool first = true;
-              for_each_replica(h, w, p.Ho, p.Wo, [&](int hp, int wp) {
-                if (first) {
-                  first = false;
-                  return;
-                }
-                bf16* dst = p.epi.outOP + op_offset(so, n, hp, wp) + blk;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(hi)[j];
-                  reinterpret_cast<uint4*>(dst + lo_off)[j] = reinterpret_cast<const uint4*>(lo)[j];
-                }
-              });
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          EPI_BARRIER();
-          if (threadIdx.x == 64 && !(p.debug & 128)) {
-            // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
-            // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
-            // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
-            if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
-            if (wantO) {
-              tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
-              tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + cc, n0);
-            }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          if (++sbuf == p.sbufs) sbuf = 0;
-        }
-        continue;  // tempty already signalled
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (CTA2)
-          mbar_arrive_leader(bar_tempty + 8 * acc);
-        else
-          mbar_arrive(bar_tempty + 8 * acc);
-      }
-    }
-    if (p.staged && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
+                            warp, lane);
   }
 
   __syncwarp();
@@ -728,6 +754,219 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   if constexpr (CTA2) cluster_sync_all();  // neither CTA frees TMEM or exits while the pair is still working
+  if (warp == 1) {
+    if constexpr (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ patch kernel
+constexpr uint32_t kDescHiPatch = (kPatchSBO >> 4) | (1u << 14) | (4u << 29);
+__device__ __forceinline__ uint64_t desc64_patch(uint32_t lo) { return ((uint64_t)kDescHiPatch << 32) | lo; }
+
+// Same roles, epilogue and CTA-pair protocol as conv_umma_kernel, but the K loop runs K-block outer /
+// tap inner over TWO rings: the patch ring (a_stages x PLANES x 12 KB, one box per K-block) and the
+// weight ring (stages x one (tap, K-block) weight block).  Input traffic from L2 and into shared
+// memory drops from 9 x 8 KB to 11.25 KB per (plane, K-block).
+template <int PLANES, int NB, int LN, bool CTA2>
+__global__ void __launch_bounds__(kThreads, 1)
+    conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmO,
+                           const UmmaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+
+  const uint32_t bar_bfull = base;            // kMaxBStages x 8 B
+  const uint32_t bar_bempty = base + 128;     // kMaxBStages x 8 B
+  const uint32_t bar_afull = base + 256;      // kMaxAStages x 8 B
+  const uint32_t bar_aempty = base + 288;     // kMaxAStages x 8 B
+  const uint32_t bar_tfull = base + 320;      // 2 x 8 B
+  const uint32_t bar_tempty = base + 336;     // 2 x 8 B
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 352);
+  const uint32_t staging0 = base + kCtrlBytes;
+  const uint32_t aring0 = staging0 + p.sbufs * kStagingBytes;
+  constexpr uint32_t a_stage_bytes = PLANES * kPatchPlane;
+  const uint32_t bring0 = aring0 + p.a_stages * a_stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t rank = 0;
+  if constexpr (CTA2) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const bool leader = rank == 0;
+  const int tile_begin = CTA2 ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
+  const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+    }
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, CTA2 ? 8 : 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    if constexpr (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 352), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 352), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t acc_stride = p.acc_stages == 2 ? 256u : 0u;
+  const int cbh = CTA2 ? p.CB / 2 : p.CB;  // B rows of one N half held by this CTA
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    // Issue order: patch of K-block g + 1, then the nine weight blocks of K-block g, so that the
+    // patch ring runs one K-block ahead of the weight ring.
+    const uint32_t a_tx = (CTA2 ? 2u : 1u) * PLANES * kPatchBytes;
+    const uint32_t b_tx = (CTA2 ? 2u : 1u) * PLANES * (uint32_t)(NB * cbh) * 64u;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int a_tile = tile_begin, a_chunk = 0;  // cursor of the patch ring
+    auto issue_patch = [&]() {
+      if (a_tile >= tile_end) return;
+      int n0, h0, w0;
+      p.g.tile_origin(a_tile, n0, h0, w0);
+      mbar_wait(bar_aempty + 8 * as, aph ^ 1);
+      if (elect_one()) {
+        const uint32_t full = bar_afull + 8 * as;
+        if (leader) mbar_expect_tx(full, a_tx);
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl) {
+          const uint32_t dst = aring0 + as * a_stage_bytes + pl * kPatchPlane;
+          if constexpr (CTA2)
+            tma_load_5d_2sm(dst, &tmP, full, 0, w0, h0, pl * p.nchunk + a_chunk, n0);
+          else
+            tma_load_5d(dst, &tmP, full, 0, w0, h0, pl * p.nchunk + a_chunk, n0);
+        }
+      }
+      __syncwarp();
+      if (++as == p.a_stages) as = 0, aph ^= 1;
+      if (++a_chunk == p.nchunk) a_chunk = 0, a_tile += gridDim.x;
+    };
+    issue_patch();
+    for (int tile = tile_begin; tile < tile_end; tile += gridDim.x) {
+      for (int chunk = 0; chunk < p.nchunk; ++chunk) {
+        issue_patch();
+        for (int tap = 0; tap < 9; ++tap) {
+          const int brow = (tap * p.nchunk + chunk) * 2 * p.Cout;
+          mbar_wait(bar_bempty + 8 * bs, bph ^ 1);
+          if (elect_one()) {
+            const uint32_t full = bar_bfull + 8 * bs;
+            if (leader) mbar_expect_tx(full, b_tx);
+            const uint32_t sb = bring0 + bs * p.b_stage_bytes;
+#pragma unroll
+            for (int pl = 0; pl < PLANES; ++pl) {
+#pragma unroll
+              for (int half = 0; half < NB; ++half) {
+                const uint32_t dst = sb + pl * p.b_plane_bytes + half * cbh * 64;
+                const int row = brow + pl * p.Cout + half * p.CB + (CTA2 ? (int)rank * cbh : 0);
+                if constexpr (CTA2)
+                  tma_load_2d_2sm(dst, &tmB, full, 0, row);
+                else
+                  tma_load_2d(dst, &tmB, full, 0, row);
+              }
+            }
+          }
+          __syncwarp();
+          if (++bs == p.stages) bs = 0, bph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.CB >> 3) << 17) |
+                           (((CTA2 ? 256u : 128u) >> 4) << 24);
+    const uint32_t a_lo0 = ((aring0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo0 = ((bring0 & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t bstage_u = p.b_stage_bytes >> 4, bplane_u = p.b_plane_bytes >> 4;
+    const uint32_t half_u = (uint32_t)(cbh * 64) >> 4;
+    const uint32_t CB = (uint32_t)p.CB;
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    int it = 0;
+    for (int tile = tile_begin; leader && tile < tile_end; tile += gridDim.x, ++it) {
+      const int acc = it % p.acc_stages;
+      const uint32_t acc_phase = (it / p.acc_stages) & 1;
+      mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * acc_stride;
+      for (int chunk = 0; chunk < p.nchunk; ++chunk) {
+        mbar_wait(bar_afull + 8 * as, aph);
+        const uint32_t a_stage_lo = a_lo0 + as * (a_stage_bytes >> 4);
+        for (int tap = 0; tap < 9; ++tap) {
+          mbar_wait(bar_bfull + 8 * bs, bph);
+          tc_fence_after();
+          if (elect_one()) {
+            // tap (a, b): start shifted by (10 a + b) rows of 64 B
+            const uint32_t a_lo = a_stage_lo + (uint32_t)((tap / 3) * kPatchW + tap % 3) * 4u;
+            const uint32_t b_lo = b_lo0 + bs * bstage_u;
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+              for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
+                // pass 0: hi*hi, 1: hi*lo, 2: lo*hi
+                const uint32_t al = a_lo + (pass == 2 ? (kPatchPlane >> 4) : 0u) + kk * 2;
+                const uint32_t bl = b_lo + (pass == 1 ? bplane_u : 0u) + kk * 2;
+#pragma unroll
+                for (int half = 0; half < NB; ++half) {
+                  const uint32_t accum = (kk | pass) ? 1u : (uint32_t)((chunk | tap) != 0);
+                  if constexpr (CTA2)
+                    umma_bf16_2sm(d0 + half * CB, desc64_patch(al), desc64(bl + half * half_u), idesc, accum);
+                  else
+                    umma_bf16(d0 + half * CB, desc64_patch(al), desc64(bl + half * half_u), idesc, accum);
+                }
+              }
+            }
+            const bool last_tap = tap == 8;
+            if constexpr (CTA2) {
+              umma_commit_2sm(bar_bempty + 8 * bs);
+              if (last_tap) umma_commit_2sm(bar_aempty + 8 * as);
+              if (last_tap && chunk == p.nchunk - 1) umma_commit_2sm(bar_tfull + 8 * acc);
+            } else {
+              umma_commit(bar_bempty + 8 * bs);
+              if (last_tap) umma_commit(bar_aempty + 8 * as);
+              if (last_tap && chunk == p.nchunk - 1) umma_commit(bar_tfull + 8 * acc);
+            }
+          }
+          __syncwarp();
+          if (++bs == p.stages) bs = 0, bph ^= 1;
+        }
+        if (++as == p.a_stages) as = 0, aph ^= 1;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
+                            warp, lane);
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if constexpr (CTA2) cluster_sync_all();
   if (warp == 1) {
     if constexpr (CTA2)
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -823,9 +1062,30 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   p.sbufs = 1;  // measured: deeper store staging does not pay for the ring stages it costs
   if (getenv("SDAB_UMMA_SBUFS")) p.sbufs = atoi(getenv("SDAB_UMMA_SBUFS"));
   SDAB_REQUIRE(p.sbufs >= 1 && p.sbufs <= 3, "staging sets out of range");
-  p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - p.sbufs * kStagingBytes) / p.stage_bytes);
-  if (p.stages > kMaxStages) p.stages = kMaxStages;
-  SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
+  // Patch kernel: plain stride-1 3x3 convolutions (the 36 block convolutions and their input-gradients)
+  // on images that tile into 8 x 16 boxes; everything else keeps one TMA box per tap.
+  static const int patch_env = getenv("SDAB_UMMA_PATCH") ? atoi(getenv("SDAB_UMMA_PATCH")) : 1;
+  p.patch = patch_env && cta2 && p.staged && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 && p.os == 1 &&
+            c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
+  if (p.patch) {
+    p.g.BW = kPatchBW, p.g.BH = kPatchBH, p.g.BN = 1;
+    p.g.tiles_w = c.W / kPatchBW, p.g.tiles_h = c.H / kPatchBH, p.g.tiles_n = c.N;
+    p.g.num_tiles = p.g.tiles_w * p.g.tiles_h * p.g.tiles_n;
+    p.b_stage_bytes = p.planes * p.b_plane_bytes;
+    const uint32_t fixed = kCtrlBytes + 1024 + p.sbufs * kStagingBytes;
+    p.a_stages = 3;
+    p.stages = (int)((kSmemBudget - fixed - p.a_stages * p.planes * kPatchPlane) / p.b_stage_bytes);
+    if (p.stages < 4) {
+      p.a_stages = 2;
+      p.stages = (int)((kSmemBudget - fixed - p.a_stages * p.planes * kPatchPlane) / p.b_stage_bytes);
+    }
+    if (p.stages > kMaxBStages) p.stages = kMaxBStages;
+    SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
+  } else {
+    p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - p.sbufs * kStagingBytes) / p.stage_bytes);
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
+  }
   p.epi = c.epi;
   {
     static const int dbg = getenv("SDAB_UMMA_DEBUG") ? atoi(getenv("SDAB_UMMA_DEBUG")) : 0;
@@ -847,7 +1107,9 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
       strides[0] = 64, strides[1] = (Wp / 2) * 64, strides[2] = (Hp / 2) * (Wp / 2) * 64,
       strides[3] = Q * Hp * Wp * 64;
     }
-    const cuuint32_t box[5] = {32, (cuuint32_t)p.g.BW, (cuuint32_t)p.g.BH, 1, (cuuint32_t)p.g.BN};
+    // patch kernel: the haloed (BW + 2) x (BH + 2) patch of one image
+    const cuuint32_t box[5] = {32, (cuuint32_t)(p.patch ? kPatchW : p.g.BW), (cuuint32_t)(p.patch ? kPatchH : p.g.BH), 1,
+                               (cuuint32_t)p.g.BN};
     SDAB_TRY(encode(&tmA, c.in, 5, dims, strides, box));
   }
   {
@@ -878,7 +1140,9 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_TRY(encode(&tmO, basep, 5, dims, strides, box));
   }
 
-  const size_t smem = kCtrlBytes + 1024 + (size_t)p.sbufs * kStagingBytes + (size_t)p.stages * p.stage_bytes;
+  const size_t smem = kCtrlBytes + 1024 + (size_t)p.sbufs * kStagingBytes +
+                      (p.patch ? (size_t)p.a_stages * p.planes * kPatchPlane + (size_t)p.stages * p.b_stage_bytes
+                               : (size_t)p.stages * p.stage_bytes);
   using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, UmmaParams);
 #define SDAB_K(P, B, L) {conv_umma_kernel<P, B, L, false>, conv_umma_kernel<P, B, L, true>}
   static const Kernel kernels[2][2][3][2] = {{{SDAB_K(1, 1, 0), SDAB_K(1, 1, 1), SDAB_K(1, 1, 2)},
@@ -886,8 +1150,16 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
                                             {{SDAB_K(2, 1, 0), SDAB_K(2, 1, 1), SDAB_K(2, 1, 2)},
                                              {SDAB_K(2, 2, 0), SDAB_K(2, 2, 1), SDAB_K(2, 2, 2)}}};
 #undef SDAB_K
+#define SDAB_KP(P, B) {conv_umma_patch_kernel<P, B, 0, true>, conv_umma_patch_kernel<P, B, 1, true>, conv_umma_patch_kernel<P, B, 2, true>}
+  static const Kernel patch_kernels[2][2][3] = {{SDAB_KP(1, 1), SDAB_KP(1, 2)}, {SDAB_KP(2, 1), SDAB_KP(2, 2)}};
+#undef SDAB_KP
   static bool attr_set = false;
   if (!attr_set) {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int l = 0; l < 3; ++l)
+          SDAB_CUDA_CHECK(
+              cudaFuncSetAttribute(patch_kernels[a][b][l], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         for (int l = 0; l < 3; ++l)
@@ -897,7 +1169,8 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     attr_set = true;
   }
   SDAB_REQUIRE(c.epi.ln >= 0 && c.epi.ln <= 2, "unknown fused LayerNorm variant");
-  const Kernel kernel = kernels[p.planes - 1][p.nb - 1][c.epi.ln][cta2 ? 1 : 0];
+  const Kernel kernel =
+      p.patch ? patch_kernels[p.planes - 1][p.nb - 1][c.epi.ln] : kernels[p.planes - 1][p.nb - 1][c.epi.ln][cta2 ? 1 : 0];
   if (cta2) {
     const int pairs = (p.g.num_tiles + 1) / 2;
     const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;

@@ -23,6 +23,8 @@ CASES = [
     (2, 96, 10, 16, 16, 1),    # final conv, C_out padded 10 -> 16
     (1, 96, 96, 2, 256, 1),    # row tiles of 128 pixels
     (5, 64, 64, 8, 8, 2),
+    (3, 96, 96, 16, 8, 1),     # patch kernel: odd number of 8 x 16 tiles (ghost tile in the last CTA pair)
+    (2, 192, 96, 32, 64, 1),   # patch kernel: several tiles per image in both directions
 ]
 
 
