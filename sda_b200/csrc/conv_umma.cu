@@ -31,6 +31,7 @@ namespace sdab {
 namespace {
 
 constexpr int kThreads = 192;
+constexpr int kPatchThreads = 320;  // patch kernel: two epilogue warpgroups (warps 2-5 and 6-9)
 constexpr uint32_t kABytes = 128 * 64;  // one A box: 128 pixels x 32 channels x bf16
 constexpr uint32_t kCtrlBytes = 1024;
 constexpr uint32_t kStageF = 128 * 128;      // epilogue staging: 128 pixels x 32 fp32 channels (SWIZZLE_128B rows)
@@ -240,8 +241,9 @@ __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-#define EPI_BARRIER() do { if (!(p.debug & 64)) epi_barrier(); } while (0)
+// named barrier of one epilogue warpgroup (ids 1 and 2; 0 is __syncthreads)
+__device__ __forceinline__ void epi_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+#define EPI_BARRIER() do { if (!(p.debug & 64)) epi_barrier(wg); } while (0)
 
 // bias / residual / activation / activation-derivative on 32 consecutive channels of one pixel
 // (same order of operations as epilogue_store16).  The residual / derivative operands are passed in
@@ -264,13 +266,26 @@ __device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = v[j];
   }
-  if (e.act) {
+  // the activation kind is uniform: branch once around straight-line loops (a per-element switch
+  // compiles to every alternative plus selects)
+  if (e.act == 1) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = act_fwd(v[j], e.act);
+    for (int j = 0; j < 32; ++j) v[j] *= sigmoid_fast(v[j]);
+  } else if (e.act == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
   if (has_dact) {
+    if (e.dact_kind == 1) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= act_bwd(rr[j], e.dact_kind);
+      for (int j = 0; j < 32; ++j) {
+        const float s = sigmoid_fast(rr[j]);
+        v[j] *= s * (1.f + rr[j] * (1.f - s));
+      }
+    } else if (e.dact_kind == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = rr[j] > 0.f ? v[j] : 0.f;
+    }
   }
   if (!e.pre) {
 #pragma unroll
@@ -322,14 +337,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
 template <int LN, bool CTA2>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
                                               uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
-                                              uint32_t acc_stride, uint32_t staging0, int tile_begin, int tile_end,
-                                              int warp, int lane) {
+                                              uint32_t acc_stride, uint32_t staging_base, int tile_begin, int tile_end,
+                                              int warp, int lane, int wg = 0, int nwg = 1) {
+  // `nwg` epilogue warpgroups take alternate tiles (warpgroup wg always drains TMEM accumulator wg), each
+  // with its own staging sets, named barrier and store-issuing thread (its first).
+  const uint32_t staging0 = staging_base + wg * p.sbufs * kStagingBytes;
+  const int issuer = 64 + 128 * wg;
   const int q = warp & 3;  // TMEM lane quarter accessible to this warp
   const int m = q * 32 + lane;
   const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
-  int it = 0;
+  int it = wg;
   int sbuf = 0;  // staging set of the next 32-channel block (running over tiles)
-  for (int tile = tile_begin; tile < tile_end; tile += gridDim.x, ++it) {
+  for (int tile = tile_begin + wg * (int)gridDim.x; tile < tile_end; tile += nwg * (int)gridDim.x, it += nwg) {
     const int acc = it % p.acc_stages;
     const uint32_t acc_phase = (it / p.acc_stages) & 1;
     int n0, h0, w0;
@@ -362,7 +381,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
       const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
       {
         // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
-        const int nt = tile + gridDim.x;
+        const int nt = tile + nwg * (int)gridDim.x;
         if (nt < p.g.num_tiles) {
           int nn0, nh0, nw0;
           p.g.tile_origin(nt, nn0, nh0, nw0);
@@ -472,7 +491,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
         if (p.debug & 32) continue;
         // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
         const uint32_t staging = staging0 + sbuf * kStagingBytes;
-        if (threadIdx.x == 64) {
+        if (threadIdx.x == issuer) {
           if (p.sbufs == 1)
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           else if (p.sbufs == 2)
@@ -489,13 +508,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
                          __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
         }
         if (wantO) {
-          __align__(16) bf16 hi[32];
-          __align__(16) bf16 lo[32];
+          uint32_t ph[16], pl[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) split_bf16(v[j], hi[j], lo[j]);
+          for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
           const uint32_t rh = staging + kStageF + m * 64, rl = rh + kStageO;
-          const uint32_t* ph = reinterpret_cast<const uint32_t*>(hi);
-          const uint32_t* pl = reinterpret_cast<const uint32_t*>(lo);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint32_t sw = (j ^ ((m >> 1) & 3)) << 4;
@@ -514,15 +530,16 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
               bf16* dst = p.epi.outOP + op_offset(so, n, hp, wp) + blk;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                reinterpret_cast<uint4*>(dst)[j] = reinterpret_cast<const uint4*>(hi)[j];
-                reinterpret_cast<uint4*>(dst + lo_off)[j] = reinterpret_cast<const uint4*>(lo)[j];
+                reinterpret_cast<uint4*>(dst)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                reinterpret_cast<uint4*>(dst + lo_off)[j] =
+                    make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
               }
             });
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         EPI_BARRIER();
-        if (threadIdx.x == 64 && !(p.debug & 128)) {
+        if (threadIdx.x == issuer && !(p.debug & 128)) {
           // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
           // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
           // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
@@ -546,7 +563,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
         mbar_arrive(bar_tempty + 8 * acc);
     }
   }
-  if (p.staged && threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (p.staged && threadIdx.x == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -771,7 +788,7 @@ __device__ __forceinline__ uint64_t desc64_patch(uint32_t lo) { return ((uint64_
 // weight ring (stages x one (tap, K-block) weight block).  Input traffic from L2 and into shared
 // memory drops from 9 x 8 KB to 11.25 KB per (plane, K-block).
 template <int PLANES, int NB, int LN, bool CTA2>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kPatchThreads, 1)
     conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmO,
                            const UmmaParams p) {
@@ -788,7 +805,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t bar_tempty = base + 336;     // 2 x 8 B
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 352);
   const uint32_t staging0 = base + kCtrlBytes;
-  const uint32_t aring0 = staging0 + p.sbufs * kStagingBytes;
+  const uint32_t aring0 = staging0 + 2 * p.sbufs * kStagingBytes;  // one staging set per epilogue warpgroup
   constexpr uint32_t a_stage_bytes = PLANES * kPatchPlane;
   const uint32_t bring0 = aring0 + p.a_stages * a_stage_bytes;
 
@@ -957,9 +974,12 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
-                            warp, lane);
+    // ===================================================================== epilogue (warps 2..5, 6..9)
+    // with a double-buffered accumulator the two warpgroups take alternate tiles
+    const int wg = (warp - 2) >> 2, nwg = (p.acc_stages == 2 && blockDim.x == kPatchThreads) ? 2 : 1;
+    if (wg < nwg)
+      epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin,
+                              tile_end, warp, lane, wg, nwg);
   }
 
   __syncwarp();
@@ -1065,6 +1085,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   // Patch kernel: plain stride-1 3x3 convolutions (the 36 block convolutions and their input-gradients)
   // on images that tile into 8 x 16 boxes; everything else keeps one TMA box per tap.
   static const int patch_env = getenv("SDAB_UMMA_PATCH") ? atoi(getenv("SDAB_UMMA_PATCH")) : 1;
+  static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
   p.patch = patch_env && cta2 && p.staged && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 && p.os == 1 &&
             c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
   if (p.patch) {
@@ -1072,7 +1093,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     p.g.tiles_w = c.W / kPatchBW, p.g.tiles_h = c.H / kPatchBH, p.g.tiles_n = c.N;
     p.g.num_tiles = p.g.tiles_w * p.g.tiles_h * p.g.tiles_n;
     p.b_stage_bytes = p.planes * p.b_plane_bytes;
-    const uint32_t fixed = kCtrlBytes + 1024 + p.sbufs * kStagingBytes;
+    const uint32_t fixed = kCtrlBytes + 1024 + 2 * p.sbufs * kStagingBytes;
     p.a_stages = 3;
     p.stages = (int)((kSmemBudget - fixed - p.a_stages * p.planes * kPatchPlane) / p.b_stage_bytes);
     if (p.stages < 4) {
@@ -1140,7 +1161,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_TRY(encode(&tmO, basep, 5, dims, strides, box));
   }
 
-  const size_t smem = kCtrlBytes + 1024 + (size_t)p.sbufs * kStagingBytes +
+  const size_t smem = kCtrlBytes + 1024 + (size_t)(p.patch ? 2 : 1) * p.sbufs * kStagingBytes +
                       (p.patch ? (size_t)p.a_stages * p.planes * kPatchPlane + (size_t)p.stages * p.b_stage_bytes
                                : (size_t)p.stages * p.stage_bytes);
   using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, UmmaParams);
@@ -1175,7 +1196,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     const int pairs = (p.g.num_tiles + 1) / 2;
     const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(p.patch && patch_wg == 2 ? kPatchThreads : kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
