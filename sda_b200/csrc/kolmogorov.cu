@@ -29,14 +29,26 @@ constexpr int kTile = 32;
 constexpr int kHalo = 2;
 constexpr int kTS = kTile + 2 * kHalo;
 
+__device__ __forceinline__ float fast_div(float a, float b) {
+  float q;
+  asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(a), "f"(b));
+  return q;
+}
+
+// Face value of c through a face with velocity uf (cl, c | cr, cn are the cells around the face):
+// upwind - (upwind - LaxWendroff) phi(r), van Leer phi(r) = 2 r / (1 + r) for r > 0, r = a / den with
+// the safe denominator den (1 when the central difference vanishes).  phi is evaluated with ONE
+// division: 2 r / (1 + r) = 2 a / (den + a), and r > 0 iff a den > 0.
 __device__ __forceinline__ float face_value(float cl, float c, float cr, float cn, float uf, float dt_h) {
   const float d = cr - c;
   const float den = d != 0.f ? d : 1.f;
-  const float r = __fdividef(uf > 0.f ? c - cl : cn - cr, den);
-  const float phi = r > 0.f ? __fdividef(2.f * r, 1.f + r) : 0.f;
-  const float upwind = uf > 0.f ? c : cr;
-  const float courant = dt_h * uf;
-  const float high = uf > 0.f ? c + 0.5f * (1.f - courant) * d : cr - 0.5f * (1.f + courant) * d;
+  const bool pos = uf > 0.f;
+  const float a = pos ? c - cl : cn - cr;
+  const float phi = a * den > 0.f ? fast_div(2.f * a, den + a) : 0.f;
+  const float upwind = pos ? c : cr;
+  // Lax-Wendroff value: c + (1 - Cn) d / 2 from the left, cr - (1 + Cn) d / 2 from the right -- the
+  // same number (cr = c + d), so one expression serves both signs
+  const float high = c + 0.5f * (1.f - dt_h * uf) * d;
   return upwind - (upwind - high) * phi;
 }
 
@@ -492,25 +504,35 @@ __global__ void __launch_bounds__(RX* RX)
     float* us = uvs + (size_t)e * 2 * N * N;
     float* vs = us + (size_t)N * N;
     float fxu_prev = 0.f, fxv_prev = 0.f, ustar_prev = 0.f;
-#pragma unroll 1
+    // sliding column windows (rows k-1 .. k+2) live in registers: one new row per iteration
+    const int jm1 = (j - 1) & mask, jp1 = (j + 1) & mask, jp2 = (j + 2) & mask;
+    const float force = sforce[j];
+    const float* pu = su + N;  // row k of the slab is pu + (k + 2) * N ...
+    const float* pv = sv + N;  //   ... i.e. these point at row k = -2
+    float um1 = pu[-N + j], u00 = pu[j], up1 = pu[N + j];
+    float vm1 = pv[-N + j], v00 = pv[j], vp1 = pv[N + j];
+#pragma unroll 2
     for (int k = -2; k < RB; ++k) {
-      const float u00 = U(k, 0), v00 = V(k, 0);
-      const float ufu = 0.5f * (u00 + U(k + 1, 0));
-      const float fxu = face_value(U(k - 1, 0), u00, U(k + 1, 0), U(k + 2, 0), ufu, dt_h) * ufu;
-      const float ufv = 0.5f * (u00 + U(k, 1));
-      const float fxv = face_value(V(k - 1, 0), v00, V(k + 1, 0), V(k + 2, 0), ufv, dt_h) * ufv;
+      const float up2 = pu[2 * N + j], vp2 = pv[2 * N + j];
+      const float ur1 = pu[jp1];
+      const float ufu = 0.5f * (u00 + up1);
+      const float fxu = face_value(um1, u00, up1, up2, ufu, dt_h) * ufu;
+      const float ufv = 0.5f * (u00 + ur1);
+      const float fxv = face_value(vm1, v00, vp1, vp2, ufv, dt_h) * ufv;
       if (k >= -1) {
-        const float vfu = 0.5f * (v00 + V(k + 1, 0));
-        const float fyu = face_value(U(k, -1), u00, U(k, 1), U(k, 2), vfu, dt_h) * vfu;
-        const float vfv = 0.5f * (v00 + V(k, 1));
-        const float fyv = face_value(V(k, -1), v00, V(k, 1), V(k, 2), vfv, dt_h) * vfv;
+        const float ul1 = pu[jm1], ur2 = pu[jp2];
+        const float vl1 = pv[jm1], vr1 = pv[jp1], vr2 = pv[jp2];
+        const float vfu = 0.5f * (v00 + vp1);
+        const float fyu = face_value(ul1, u00, ur1, ur2, vfu, dt_h) * vfu;
+        const float vfv = 0.5f * (v00 + vr1);
+        const float fyv = face_value(vl1, v00, vr1, vr2, vfv, dt_h) * vfv;
         float fyu_m = __shfl_up_sync(0xffffffffu, fyu, 1), fyv_m = __shfl_up_sync(0xffffffffu, fyv, 1);
         if (lane == 0) fyu_m = fyb[warp * (RB + 1) + k + 1], fyv_m = fyb[(NW + warp) * (RB + 1) + k + 1];
         const float conv_u = -((fxu - fxu_prev) + (fyu - fyu_m)) * inv_h;
-        const float lap_u = (U(k + 1, 0) + U(k - 1, 0) + U(k, 1) + U(k, -1) - 4.f * u00) * inv_h2;
-        const float ustar = u00 + dt * (conv_u + nu * lap_u + (sforce[j] - 0.1f * u00));
+        const float lap_u = (up1 + um1 + ur1 + ul1 - 4.f * u00) * inv_h2;
+        const float ustar = u00 + dt * (conv_u + nu * lap_u + (force - 0.1f * u00));
         const float conv_v = -((fxv - fxv_prev) + (fyv - fyv_m)) * inv_h;
-        const float lap_v = (V(k + 1, 0) + V(k - 1, 0) + V(k, 1) + V(k, -1) - 4.f * v00) * inv_h2;
+        const float lap_v = (vp1 + vm1 + vr1 + vl1 - 4.f * v00) * inv_h2;
         const float vstar = v00 + dt * (conv_v + nu * lap_v - 0.1f * v00);
         const float vleft = __shfl_up_sync(0xffffffffu, vstar, 1);
         if (k >= 0) {
@@ -526,6 +548,9 @@ __global__ void __launch_bounds__(RX* RX)
         ustar_prev = ustar;
       }
       fxu_prev = fxu, fxv_prev = fxv;
+      um1 = u00, u00 = up1, up1 = up2;
+      vm1 = v00, v00 = vp1, vp1 = vp2;
+      pu += N, pv += N;
     }
     __syncthreads();
     if (tid < NW * RB) {
@@ -748,15 +773,17 @@ int inner_step_fast(const sdab_kolmogorov* k, float* uv, float* uvs, float2* spe
   return SDAB_OK;
 }
 
-// The ensemble is walked in chunks of (an even number of) members whose working set -- state,
-// u*/v* and the pair spectra, 20 N^2 bytes per member -- stays resident in the 126 MB L2 for all
-// inner steps of all transitions; members are independent, so the order does not change results.
+// The ensemble can be walked in chunks of (an even number of) members whose working set -- state,
+// u*/v* and the pair spectra, 20 N^2 bytes per member -- stays resident in the 126 MB L2
+// (SDAB_KOLMO_L2_MB); members are independent, so the order does not change results.  Measured on
+// B200: the kernels are latency- rather than bandwidth-bound and the smaller grids of a chunked walk
+// cost more than the L2 hits save, so the default is one chunk.
 int transition_fast(const sdab_kolmogorov* k, float* uv, int E, int n_transitions, float* traj, const KWs& w,
                     cudaStream_t st) {
   const int N = k->N;
   const size_t n2 = (size_t)N * N, state = (size_t)E * 2 * n2;
-  static const int chunk_mb = env_int("SDAB_KOLMO_L2_MB", 88);
-  static const int rb256 = env_int("SDAB_KOLMO_RB", 16);
+  static const int chunk_mb = env_int("SDAB_KOLMO_L2_MB", 1 << 20);
+  static const int rb256 = env_int("SDAB_KOLMO_RB", 8);
   int chunk = (int)((size_t)chunk_mb * 1024 * 1024 / (20 * n2));
   chunk = chunk < 2 ? 2 : chunk & ~1;
   for (int e0 = 0; e0 < E; e0 += chunk) {
