@@ -243,7 +243,7 @@ __device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
 }
 // named barrier of one epilogue warpgroup (ids 1 and 2; 0 is __syncthreads)
 __device__ __forceinline__ void epi_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
-#define EPI_BARRIER() do { if (!(p.debug & 64)) epi_barrier(wg); } while (0)
+#define EPI_BARRIER() do { if (!(p.debug & 64)) epi_barrier(bar_id); } while (0)
 
 // bias / residual / activation / activation-derivative on 32 consecutive channels of one pixel
 // (same order of operations as epilogue_store16).  The residual / derivative operands are passed in
@@ -338,11 +338,15 @@ template <int LN, bool CTA2>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
                                               uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
                                               uint32_t acc_stride, uint32_t staging_base, int tile_begin, int tile_end,
-                                              int warp, int lane, int wg = 0, int nwg = 1) {
-  // `nwg` epilogue warpgroups take alternate tiles (warpgroup wg always drains TMEM accumulator wg), each
-  // with its own staging sets, named barrier and store-issuing thread (its first).
+                                              int warp, int lane, int wg = 0, int nwg = 1, bool csplit = false) {
+  // `nwg` epilogue warpgroups, each with its own staging sets, named barrier and store-issuing thread (its
+  // first).  They take alternate tiles (warpgroup wg always drains TMEM accumulator wg), or -- csplit, for
+  // the single-accumulator case (C_out > 256) without LayerNorm -- alternate 32-channel blocks of every tile.
   const uint32_t staging0 = staging_base + wg * p.sbufs * kStagingBytes;
   const int issuer = 64 + 128 * wg;
+  const int cc0 = csplit ? wg : 0, ccstep = csplit ? nwg : 1;
+  if (csplit) wg = 0, nwg = 1;  // tile walk of a single warpgroup
+  const int bar_id = issuer >> 7;  // == original wg
   const int q = warp & 3;  // TMEM lane quarter accessible to this warp
   const int m = q * 32 + lane;
   const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
@@ -450,7 +454,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
         st_a = sg * invC, st_b = sga * invC1;
         st_r = valid ? p.epi.ln_rstd_in[pix] : 1.f;
       }
-      for (int cc = 0; cc < p.out_chunks; ++cc) {
+      for (int cc = cc0; cc < p.out_chunks; cc += ccstep) {
         float v[32], f[32], rr[32], aa[32];
         // operands from global memory first: their latency overlaps the accumulator load
         if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
@@ -460,7 +464,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           load32_hilo(ah, ah + so.lo_offset(), aa);
         }
         tmem_ld32(t0 + cc * 32, v);
-        if (cc == p.out_chunks - 1) {
+        if (cc + ccstep >= p.out_chunks) {
           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -815,6 +819,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const bool leader = rank == 0;
   const int tile_begin = CTA2 ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
   const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
+  // single accumulator (C_out > 256), no LayerNorm: the two epilogue warpgroups split every tile's channel blocks
+  const bool csplit = LN == 0 && p.acc_stages == 1 && blockDim.x == kPatchThreads;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, CTA2 ? 8 : 4);
+      mbar_init(bar_tempty + 8 * a, (CTA2 ? 8 : 4) * (csplit ? 2 : 1));  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -976,10 +982,10 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   } else {
     // ===================================================================== epilogue (warps 2..5, 6..9)
     // with a double-buffered accumulator the two warpgroups take alternate tiles
-    const int wg = (warp - 2) >> 2, nwg = (p.acc_stages == 2 && blockDim.x == kPatchThreads) ? 2 : 1;
+    const int wg = (warp - 2) >> 2, nwg = ((p.acc_stages == 2 || csplit) && blockDim.x == kPatchThreads) ? 2 : 1;
     if (wg < nwg)
       epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin,
-                              tile_end, warp, lane, wg, nwg);
+                              tile_end, warp, lane, wg, nwg, csplit);
   }
 
   __syncwarp();
