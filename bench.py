@@ -308,7 +308,7 @@ def run_ours(args, rank, local_rank, world):
                 'd2h_bytes_per_step': x_pin.numel() * 4},
         'gpu_launches': int(launches),
         'roofline': {
-            'bound': 'tensor', 'kernel': 'conv_umma_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
+            'bound': 'tensor', 'kernel': 'conv_umma_patch_kernel (+ conv_umma_kernel for strided / sub-pixel layers)', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
             'note': f'algorithmic FLOPs (one multiply-add pair per product) over CUDA-event kernel time of {conv_launches.value} '
                     f'launches on rank 0; the {passes}-pass mode issues {passes}x that many tensor-core FLOPs '

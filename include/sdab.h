@@ -94,7 +94,8 @@ int sdab_unet_set_weights(sdab_unet* h, const float* const* conv_w_host, const f
                           const float* const* proj_w_host, const float* const* proj_b_host, void* packed,
                           size_t packed_bytes, void* stream);
 
-/* Workspace needed for N images of H x W.  save != 0 keeps what dgrad needs. */
+/* Workspace needed for N images of H x W.  save = 1 keeps what dgrad needs, save = 2 what
+ * sdab_unet_backward (parameter gradients) needs as well. */
 size_t sdab_unet_workspace_bytes(const sdab_unet* h, int N, int H, int W, int save);
 
 /* UNet.forward(x, y)  nn.py:184-206.
@@ -107,6 +108,22 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
  * reference UNet in GaussianScore.forward, score.py:381-394). */
 int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
                     int engine, void* stream);
+
+/* Training backward (reference: what loss.backward() computes through UNet in VPSDE.loss,
+ * sda/score.py:265-276, driven by sda/utils.py:136-143): the input-gradient of sdab_unet_dgrad
+ * plus the gradients of every convolution weight and bias and of the time-shift table, for
+ * the last forward run with save = 2 on the same workspace.
+ * conv_dw_host[i]: (C_out, C_in, 3, 3), conv_db_host[i]: (C_out) in the order of
+ * sdab_unet_set_weights (host arrays of device pointers; overwritten);
+ * dshift: (Nt, sdab_unet_shift_rows) = d loss / d (proj_w[j] y + proj_b[j]) for the blocks in
+ * order, from which the caller derives the gradients of the projection Linears
+ * (nn.py:132-135) and of y.  Weight gradients run on the fp32 CUDA cores (first path);
+ * partial sums are combined with floating-point atomics. */
+int sdab_unet_backward(sdab_unet* h, const float* gout, float* gx, float* const* conv_dw_host,
+                       float* const* conv_db_host, float* dshift, void* workspace, size_t workspace_bytes, int mode,
+                       int engine, void* stream);
+/* Rows of the shift table: sum of the channels of all modulated blocks. */
+int sdab_unet_shift_rows(const sdab_unet* h);
 
 /* One 3x3 circular convolution on NCHW fp32 tensors (nn.Conv2d(kernel_size=3, padding=1,
  * padding_mode='circular', stride), sda/nn.py:125-128,151-157).  weight: (Cout, Cin, 3, 3); bias:

@@ -53,6 +53,9 @@ _PROTOTYPES = {
     'sdab_unet_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_size_t, c_int, c_int, c_int, c_void_p]),
     'sdab_unet_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    'sdab_unet_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
+                                   c_int, c_void_p]),
+    'sdab_unet_shift_rows': (c_int, [c_void_p]),
     'sdab_conv3x3_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     'sdab_conv3x3': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_int, c_void_p, c_size_t, c_void_p]),

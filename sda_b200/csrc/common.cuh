@@ -190,6 +190,26 @@ struct ConvProblem {
   ConvEpilogue epi;
 };
 
+// Weight / bias gradient of one 3x3 circular convolution (csrc/wgrad.cu): dw (cout, cin, 3, 3) and db (cout)
+// are ACCUMULATED into (atomics over pixel splits) -- the caller zero-fills them.
+struct WgradProblem {
+  const float* gF;  // cotangent of the convolution output: F(Cg) at the output resolution, or null ...
+  const bf16* gOP;  // ... or as an operand tensor OP(Cg), normal layout
+  const bf16* xOP;  // convolution input as operand tensor OP(Cx): x_kind 0 normal layout (stride 1), 1 parity layout
+                    // of the (2H) x (2W) input (stride 2), 2 at HALF the output resolution (nearest x2 folded in)
+  const float* xF;  // x_kind 3: F(Cx) at the output resolution, activation `act` applied on load
+  int x_kind, act;
+  int N, H, W;      // OUTPUT resolution
+  int Cg, Cx;       // (padded) channel counts of the g and x tensors
+  int cout, cin;    // real channel counts
+  float* dw;
+  float* db;        // or null
+};
+int conv3x3_wgrad(const WgradProblem& p, cudaStream_t stream);
+// dshift[(Nt > 1 ? n : 0) * stride + c] += sum_{h, w} (a - b)[n, h, w, c]   (F(C) tensors)
+int shift_grad(const float* a, const float* b, float* dshift, int stride, int Nt, int N, int H, int W, int C,
+               cudaStream_t stream);
+
 int conv3x3_simt(const ConvProblem& p, cudaStream_t stream);
 int conv3x3_umma(const ConvProblem& p, cudaStream_t stream);
 

@@ -68,6 +68,7 @@ struct UmmaParams {
   int patch;       // patch kernel: one haloed input patch per K-block serves all nine taps
   int a_stages;    // patch kernel: depth of the patch ring (`stages` is the depth of the weight ring)
   uint32_t b_stage_bytes;
+  int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
@@ -820,7 +821,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const int tile_begin = CTA2 ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
   const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
   // single accumulator (C_out > 256), no LayerNorm: the two epilogue warpgroups split every tile's channel blocks
-  const bool csplit = LN == 0 && p.acc_stages == 1 && blockDim.x == kPatchThreads;
+  const bool csplit = LN == 0 && (p.acc_stages == 1 || p.csplit) && blockDim.x == kPatchThreads;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -1092,6 +1093,8 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   // on images that tile into 8 x 16 boxes; everything else keeps one TMA box per tap.
   static const int patch_env = getenv("SDAB_UMMA_PATCH") ? atoi(getenv("SDAB_UMMA_PATCH")) : 1;
   static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
+  static const int csplit_env = getenv("SDAB_UMMA_CSPLIT") ? atoi(getenv("SDAB_UMMA_CSPLIT")) : 0;
+  p.csplit = csplit_env;
   p.patch = patch_env && cta2 && p.staged && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 && p.os == 1 &&
             c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
   if (p.patch) {

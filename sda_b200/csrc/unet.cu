@@ -55,7 +55,8 @@ struct sdab_unet {
   std::vector<std::vector<int>> desc_blk, asc_blk;        // block ids
   // saved forward
   bool saved = false;
-  int sN = 0, sH = 0, sW = 0;
+  int saved_level = 0;  // 1: input-gradient, 2: + parameter gradients
+  int sN = 0, sNt = 0, sH = 0, sW = 0;
   void* sws = nullptr;
 };
 
@@ -72,13 +73,14 @@ struct Plan {
   // backward temporaries
   size_t gout_op, gxf;
   std::vector<size_t> gc1op, gup, gz;
+  std::vector<size_t> xs2g;  // training: the tail transposes' parity operand (xs2 itself feeds the heads' wgrad)
   size_t total;
 };
 
 size_t f_bytes(int N, int H, int W, int C) { return (size_t)N * H * W * C * sizeof(float); }
 size_t op_bytes(int N, int H, int W, int C) { return OpShape{N, H, W, C, 0}.bytes(); }
 
-Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save) {
+Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save, bool train = false) {
   Plan p;
   const int D = h->d.depth;
   p.D = D;
@@ -90,6 +92,7 @@ Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save) {
   p.outf = a.take(f_bytes(N, H, W, nout));
   p.x0.resize(D), p.x1.resize(D), p.skip.resize(D), p.hop.resize(D), p.xs2.resize(D), p.aop_tmp.resize(D);
   p.upop.assign(D, 0), p.rstd_tail.assign(D, 0), p.gc1op.assign(D, 0), p.gup.assign(D, 0), p.gz.assign(D, 0);
+  p.xs2g.assign(D, 0);
   for (int d = 0; d < D; ++d) {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
     p.x0[d] = a.take(f_bytes(N, Hd, Wd, C));
@@ -123,6 +126,7 @@ Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save) {
     for (int d = 0; d < D; ++d) {
       const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
       p.gc1op[d] = a.take(op_bytes(N, Hd, Wd, C));
+      p.xs2g[d] = train && d < D - 1 ? a.take(op_bytes(N, Hd, Wd, C)) : p.xs2[d];
       if (d > 0) {
         p.gup[d] = a.take(f_bytes(N, 2 * Hd, 2 * Wd, C));
         p.gz[d] = a.take(op_bytes(N, 2 * Hd, 2 * Wd, C));
@@ -277,7 +281,7 @@ int sdab_unet_set_weights(sdab_unet* h, const float* const* conv_w, const float*
 size_t sdab_unet_workspace_bytes(const sdab_unet* h, int N, int H, int W, int save) {
   if (!h || N < 1) return 0;
   // Nt <= N: size the shift table for the per-sample case
-  return make_plan(h, N, N, H, W, save != 0).total;
+  return make_plan(h, N, N, H, W, save != 0, save == 2).total;
 }
 
 int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
@@ -289,7 +293,7 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
   SDAB_REQUIRE(engine == SDAB_ENGINE_UMMA || engine == SDAB_ENGINE_SIMT, "unknown engine");
   SDAB_TRY(check_shape(h, N, H, W));
   SDAB_TRY(sdab_device_check());
-  const Plan p = make_plan(h, N, N, H, W, save != 0);
+  const Plan p = make_plan(h, N, N, H, W, save != 0, save == 2);
   SDAB_REQUIRE(workspace_bytes >= p.total, "workspace too small");
   SDAB_REQUIRE(((uintptr_t)workspace & 1023) == 0, "workspace must be 1024-byte aligned");
 
@@ -431,21 +435,34 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
     }
   }
   if (save) {
-    h->saved = true;
-    h->sN = N, h->sH = H, h->sW = W, h->sws = workspace;
+    h->saved = true, h->saved_level = save == 2 ? 2 : 1;
+    h->sN = N, h->sNt = Nt, h->sH = H, h->sW = W, h->sws = workspace;
   }
   return SDAB_OK;
 }
 
-int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
-                    int engine, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// parameter-gradient targets of the training backward (host arrays of device pointers)
+struct WTargets {
+  float* const* dw;
+  float* const* db;
+  float* dshift;
+};
+
+int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
+                  int engine, void* stream, const WTargets* wt) {
   SDAB_REQUIRE(h && gout && gx && workspace, "null argument");
   if (!h->saved || h->sws != workspace)
-    return fail(SDAB_ERR_STATE, "sdab_unet_dgrad needs a preceding sdab_unet_forward(save=1) on the same workspace");
+    return fail(SDAB_ERR_STATE, "the backward pass needs a preceding sdab_unet_forward(save != 0) on the same workspace");
+  if (wt && h->saved_level != 2)
+    return fail(SDAB_ERR_STATE, "parameter gradients need sdab_unet_forward(save = 2)");
   SDAB_REQUIRE(mode == SDAB_MODE_BF16X3 || mode == SDAB_MODE_BF16, "unknown mode");
   SDAB_REQUIRE(engine == SDAB_ENGINE_UMMA || engine == SDAB_ENGINE_SIMT, "unknown engine");
-  const int N = h->sN, H = h->sH, W = h->sW;
-  const Plan p = make_plan(h, N, N, H, W, true);
+  const int N = h->sN, Nt = h->sNt, H = h->sH, W = h->sW;
+  const Plan p = make_plan(h, N, N, H, W, true, h->saved_level == 2);
   SDAB_REQUIRE(workspace_bytes >= p.total, "workspace too small");
 
   cudaStream_t st = (cudaStream_t)stream;
@@ -462,13 +479,35 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
   auto GA = [&](int d) { return F(p.skip[d]); };
   auto GOP = [&](int d) { return OP(p.hop[d]); };
 
+  if (wt) {
+    for (size_t i = 0; i < h->convs.size(); ++i) {
+      SDAB_TRY(fill_zero(wt->dw[i], (size_t)h->convs[i].cout * h->convs[i].cin * 9 * sizeof(float), st));
+      SDAB_TRY(fill_zero(wt->db[i], (size_t)h->convs[i].cout * sizeof(float), st));
+    }
+    SDAB_TRY(fill_zero(wt->dshift, (size_t)Nt * h->shift_rows * sizeof(float), st));
+  }
+  // weight / bias gradient of convolution ci (no-op outside training)
+  auto wgrad = [&](int ci, const float* gF, const bf16* gOP, int Cg, const bf16* xOP, const float* xF, int x_kind,
+                   int Cx, int Ho, int Wo) -> int {
+    if (!wt) return SDAB_OK;
+    WgradProblem w{};
+    w.gF = gF, w.gOP = gOP, w.xOP = xOP, w.xF = xF, w.x_kind = x_kind, w.act = act;
+    w.N = N, w.H = Ho, w.W = Wo, w.Cg = Cg, w.Cx = Cx, w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin;
+    w.dw = wt->dw[ci], w.db = wt->db[ci];
+    return conv3x3_wgrad(w, st);
+  };
+
   // backward of one block: cur (F, operand in GOP[d]) -> other ping-pong buffer (+ GOP[d])
   auto block_bwd = [&](int d, int j, int c1, const float* cur, float* dst) -> int {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
+    // conv2: output cotangent = cur, input = act(saved pre-activation)
+    SDAB_TRY(wgrad(c1 + 1, cur, nullptr, C, nullptr, F(p.c1[j]), 3, C, Hd, Wd));
     ConvProblem q{};
     q.in = GOP(d), q.wpk = wb(c1 + 1), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = C, q.stride = 1, q.mode = mode;
     q.epi.dact = F(p.c1[j]), q.epi.dact_kind = act, q.epi.outOP = OP(p.gc1op[d]);
     SDAB_TRY(run_conv(engine, q, st));
+    // conv1: output cotangent = gC1 (operand tensor), input = the saved LayerNorm output
+    SDAB_TRY(wgrad(c1, nullptr, OP(p.gc1op[d]), C, OP(p.aop[j]), nullptr, 0, C, Hd, Wd));
     ConvProblem r{};
     r.in = OP(p.gc1op[d]), r.wpk = wb(c1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
     r.mode = mode;
@@ -476,11 +515,16 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       // LayerNorm adjoint + residual fused into the epilogue of conv1^T (ConvEpilogue::ln == 2)
       r.epi.ln = 2, r.epi.ln_a = OP(p.aop[j]), r.epi.ln_rstd_in = F(p.rstd[j]);
       r.epi.res = cur, r.epi.outF = dst, r.epi.outOP = GOP(d);
-      return run_conv(engine, r, st);
+      SDAB_TRY(run_conv(engine, r, st));
+    } else {
+      r.epi.outF = GA(d);
+      SDAB_TRY(run_conv(engine, r, st));
+      SDAB_TRY(ln_backward(GA(d), OP(p.aop[j]), F(p.rstd[j]), cur, dst, GOP(d), N, Hd, Wd, C, 0, st));
     }
-    r.epi.outF = GA(d);
-    SDAB_TRY(run_conv(engine, r, st));
-    return ln_backward(GA(d), OP(p.aop[j]), F(p.rstd[j]), cur, dst, GOP(d), N, Hd, Wd, C, 0, st);
+    // the shift enters through the LayerNorm only: its cotangent is dst - cur summed over the pixels
+    if (wt)
+      SDAB_TRY(shift_grad(dst, cur, wt->dshift + h->block_shift_off[j], h->shift_rows, Nt, N, Hd, Wd, C, st));
+    return SDAB_OK;
   };
 
   const int kout = round_up(h->d.out_channels, 32);
@@ -491,6 +535,7 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
     ConvProblem q{};
     q.in = OP(p.gout_op), q.wpk = wb(ci), q.N = N, q.H = H, q.W = W, q.Cin = kout, q.Cout = h->d.hidden_channels[0];
     q.stride = 1, q.mode = mode, q.epi.outF = G0(0), q.epi.outOP = GOP(0);
+    SDAB_TRY(wgrad(ci, nullptr, OP(p.gout_op), kout, OP(p.finop), nullptr, 0, h->d.hidden_channels[0], H, W));
     SDAB_TRY(run_conv(engine, q, st, h->d.out_channels));
     cur = G0(0);
   }
@@ -508,9 +553,11 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       gskip[d] = cur;
       const int ci = h->tail_conv[d + 1];
       const int Cn = h->d.hidden_channels[d + 1];
-      SDAB_TRY(f_to_operand(cur, OP(p.xs2[d]), N, Hd, Wd, C, 1, st));
+      // tail conv: output cotangent = cur, input = nearest x2 of the saved low-resolution LayerNorm output
+      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.upop[d + 1]), nullptr, 2, Cn, Hd, Wd));
+      SDAB_TRY(f_to_operand(cur, OP(p.xs2g[d]), N, Hd, Wd, C, 1, st));
       ConvProblem q{};
-      q.in = OP(p.xs2[d]), q.in_s2 = 1, q.wpk = (const bf16*)(pk + h->convs[ci].off_tb), q.wtaps = 16;
+      q.in = OP(p.xs2g[d]), q.in_s2 = 1, q.wpk = (const bf16*)(pk + h->convs[ci].off_tb), q.wtaps = 16;
       q.N = N, q.H = Hd / 2, q.W = Wd / 2, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
       q.taps.n = 16;
       for (int t = 0; t < 16; ++t) {
@@ -526,6 +573,7 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       gskip[d] = cur;
       const int ci = h->tail_conv[d + 1];
       const int Cn = h->d.hidden_channels[d + 1];
+      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.upop[d + 1]), nullptr, 0, Cn, Hd, Wd));
       ConvProblem q{};
       q.in = GOP(d), q.wpk = wb(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
       q.epi.outF = F(p.gup[d + 1]);
@@ -543,6 +591,12 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
       cur = dst;
     }
     const int ci = h->head_conv[d];
+    // head conv: output cotangent = cur; input = the level below in the parity layout (stride 2), or the
+    // packed network input
+    if (d > 0)
+      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.xs2[d - 1]), nullptr, 1, h->d.hidden_channels[d - 1], Hd, Wd));
+    else
+      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.in_op), nullptr, 0, round_up(h->d.in_channels, 32), Hd, Wd));
     if (d > 0 && engine == SDAB_ENGINE_UMMA) {
       // transpose of the stride-2 head by output parity: gx[2i + po, 2j + pp] only receives the taps
       // with a = po + 1 (mod 2), b = pp + 1 (mod 2) -- 1, 2, 2 and 4 taps instead of 9 on a
@@ -584,5 +638,24 @@ int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace,
   }
   return SDAB_OK;
 }
+
+}  // namespace
+
+extern "C" {
+
+int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
+                    int engine, void* stream) {
+  return backward_impl(h, gout, gx, workspace, workspace_bytes, mode, engine, stream, nullptr);
+}
+
+int sdab_unet_backward(sdab_unet* h, const float* gout, float* gx, float* const* conv_dw_host,
+                       float* const* conv_db_host, float* dshift, void* workspace, size_t workspace_bytes, int mode,
+                       int engine, void* stream) {
+  SDAB_REQUIRE(conv_dw_host && conv_db_host && dshift, "null argument");
+  const WTargets wt{conv_dw_host, conv_db_host, dshift};
+  return backward_impl(h, gout, gx, workspace, workspace_bytes, mode, engine, stream, &wt);
+}
+
+int sdab_unet_shift_rows(const sdab_unet* h) { return h ? h->shift_rows : 0; }
 
 }  // extern "C"

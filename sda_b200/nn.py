@@ -127,43 +127,38 @@ def _engine() -> int:
     return _lib.ENGINE_UMMA if name == 'umma' else _lib.ENGINE_SIMT
 
 
-class _RaiseOnBackward(torch.autograd.Function):
-    r"""Identity whose backward raises: gradients w.r.t. the modulation vector (hence
-    w.r.t. any parameter) are a next-tier row, and must not be
-    silently dropped."""
-
-    @staticmethod
-    def forward(ctx, y):
-        return y.view_as(y)
-
-    @staticmethod
-    def backward(ctx, g):
-        raise NotImplementedError(
-            'sda_b200.nn.UNet computes input gradients only (guided sampling); parameter / '
-            'modulation gradients (training, SURVEY.md section 8f) are not implemented yet'
-        )
-
-
 class _UNetFunction(torch.autograd.Function):
-    r"""UNet.forward / input-VJP through libsdab (sdab_unet_forward / sdab_unet_dgrad)."""
+    r"""UNet.forward and its backward through libsdab.
+
+    Guided sampling differentiates w.r.t. the input only (sdab_unet_forward(save=1) /
+    sdab_unet_dgrad); when a parameter or the modulation vector requires a gradient (training,
+    VPSDE.loss -> sda/utils.py:loop) the forward saves the training state (save=2) and the
+    backward is sdab_unet_backward: input, convolution weight / bias and shift-table gradients
+    from the library, the gradients of the projection Linears and of y derived from the latter.
+    `params` are the parameters in the library's order ((weight, bias) of every convolution, then
+    of every projection) so that autograd routes their gradients."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, y: Tensor, net: 'UNet') -> Tensor:
-        save = bool(ctx.needs_input_grad[0])
+    def forward(ctx, x: Tensor, y: Tensor, net: 'UNet', *params: Tensor) -> Tensor:
+        train = any(ctx.needs_input_grad[1:])
+        save = 2 if train else int(bool(ctx.needs_input_grad[0]))
         out = net._native_forward(x, y, save)
         ctx.net = net
         ctx.save = save
-        ctx.y_shape = y.shape
         ctx.token = net._forward_token
+
+        if train:
+            ctx.save_for_backward(y.detach())
 
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
         net = ctx.net
+        nparams = len(ctx.needs_input_grad) - 3
 
         if not ctx.save:
-            return None, None, None
+            return (None,) * (3 + nparams)
 
         if ctx.token != net._forward_token:
             raise RuntimeError(
@@ -171,10 +166,30 @@ class _UNetFunction(torch.autograd.Function):
                 'overwritten by a later forward of the same module'
             )
 
-        gx = net._native_dgrad(g)
-        gy = g.new_zeros(ctx.y_shape) if ctx.needs_input_grad[1] else None
+        if ctx.save == 1:
+            return (net._native_dgrad(g), None, None) + (None,) * nparams
 
-        return gx, gy, None
+        (y,) = ctx.saved_tensors
+        gx, conv_grads, dshift = net._native_backward(g, y.reshape(-1, y.shape[-1]).shape[0])
+        convs, projs = net._ordered_parameters()
+        y2 = y.reshape(-1, y.shape[-1]).to(torch.float32)
+        proj_grads, gy, off = [], torch.zeros_like(y2), 0
+
+        for m in projs:
+            ds = dshift[:, off:off + m.out_features]
+            proj_grads += [ds.t() @ y2, ds.sum(dim=0)]
+            gy = gy + ds @ m.weight.detach()
+            off += m.out_features
+
+        grads = conv_grads + proj_grads
+        grads = [gr if need else None for gr, need in zip(grads, ctx.needs_input_grad[3:])]
+
+        return (
+            gx if ctx.needs_input_grad[0] else None,
+            gy.reshape(y.shape) if ctx.needs_input_grad[1] else None,
+            None,
+            *grads,
+        )
 
 
 class UNet(nn.Module):
@@ -445,14 +460,39 @@ class UNet(nn.Module):
 
         return gx
 
+    def _native_backward(self, g: Tensor, Nt: int):
+        r"""sdab_unet_backward: (gx, [dW_0, db_0, dW_1, ...] in the library's convolution order, dshift)."""
+
+        with torch.cuda.device(g.device):
+            lib = _lib.load()
+            g = g.detach().to(torch.float32).contiguous()
+            N, _, H, W = g.shape
+            ws = self._workspace
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            gx = torch.empty((N, self.in_channels, H, W), dtype=torch.float32, device=g.device)
+            convs, _ = self._ordered_parameters()
+            dws = [torch.empty_like(m.weight, dtype=torch.float32).contiguous() for m in convs]
+            dbs = [torch.empty_like(m.bias, dtype=torch.float32) for m in convs]
+            dshift = torch.empty((Nt, lib.sdab_unet_shift_rows(self._handle)), dtype=torch.float32, device=g.device)
+            pw = (ctypes.c_void_p * len(convs))(*[t.data_ptr() for t in dws])
+            pb = (ctypes.c_void_p * len(convs))(*[t.data_ptr() for t in dbs])
+            _lib.check(
+                lib.sdab_unet_backward(
+                    self._handle, g.data_ptr(), gx.data_ptr(), pw, pb, dshift.data_ptr(), base,
+                    ws.numel() - (base - ws.data_ptr()), self._saved_mode[0], self._saved_mode[1], _lib.stream_ptr(),
+                )
+            )
+
+        return gx, [t for pair in zip(dws, dbs) for t in pair], dshift
+
     def forward(self, x: Tensor, y: Tensor) -> Tensor:
         if not self._native:
             return self._module_forward(x, y)
 
-        if torch.is_grad_enabled() and y.requires_grad:
-            y = _RaiseOnBackward.apply(y)
+        convs, projs = self._ordered_parameters()
+        params = [p for m in convs + projs for p in (m.weight, m.bias)]
 
-        return _UNetFunction.apply(x, y, self)
+        return _UNetFunction.apply(x, y, self, *params)
 
     def __del__(self):
         handle = getattr(self, '_handle', None)
