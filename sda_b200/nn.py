@@ -16,8 +16,10 @@ PyTorch by design and never touch the library.
 
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
+import threading
 from typing import Callable, Sequence, Union
 
 import torch
@@ -127,6 +129,25 @@ def _engine() -> int:
     return _lib.ENGINE_UMMA if name == 'umma' else _lib.ENGINE_SIMT
 
 
+_scope = threading.local()
+
+
+@contextlib.contextmanager
+def input_gradient_only():
+    r"""Inside this context the native U-Net differentiates w.r.t. its input only, even though its
+    parameters require gradients: the likelihood guidance (GaussianScore / DPSGaussianScore,
+    sda/score.py:381-394) asks autograd for d log p / d x alone, and a custom Function cannot see
+    which of its inputs a torch.autograd.grad call is after."""
+
+    prev = getattr(_scope, 'input_only', False)
+    _scope.input_only = True
+
+    try:
+        yield
+    finally:
+        _scope.input_only = prev
+
+
 class _UNetFunction(torch.autograd.Function):
     r"""UNet.forward and its backward through libsdab.
 
@@ -140,7 +161,7 @@ class _UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, y: Tensor, net: 'UNet', *params: Tensor) -> Tensor:
-        train = any(ctx.needs_input_grad[1:])
+        train = any(ctx.needs_input_grad[1:]) and not getattr(_scope, 'input_only', False)
         save = 2 if train else int(bool(ctx.needs_input_grad[0]))
         out = net._native_forward(x, y, save)
         ctx.net = net
@@ -278,6 +299,7 @@ class UNet(nn.Module):
         self._packed_key = None
         self._workspace = None
         self._forward_token = 0
+        self._saved_level = 0
 
     # ------------------------------------------------------------------ reference module-tree forward
     def _module_forward(self, x: Tensor, y: Tensor) -> Tensor:
@@ -433,6 +455,7 @@ class UNet(nn.Module):
             out = torch.empty((N, self.out_channels, H, W), dtype=torch.float32, device=x.device)
             self._forward_token += 1
             self._saved_mode = (_mode(), _engine())
+            self._saved_level = int(save)
             _lib.check(
                 lib.sdab_unet_forward(
                     self._handle, x.data_ptr(), y.data_ptr(), Nt, N, H, W, out.data_ptr(), base,

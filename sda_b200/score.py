@@ -30,7 +30,7 @@ from torch import Size, Tensor
 
 from . import _lib
 from .nn import *  # noqa: F401,F403  (the reference re-exports sda.nn from sda.score)
-from .nn import ResMLP, UNet
+from .nn import ResMLP, UNet, input_gradient_only
 
 try:  # progress bar as in the reference (sda/score.py:250); optional here
     from tqdm import tqdm
@@ -464,7 +464,9 @@ class DPSGaussianScore(nn.Module):
         with torch.enable_grad():
             x = x.detach().requires_grad_(True)
 
-            eps = self.sde.eps(x, t)
+            with input_gradient_only():
+                eps = self.sde.eps(x, t)
+
             x_ = _tweedie(x, eps, mu, sigma)
             err = (self.y - self.A(x_)).square().sum()
 
@@ -509,7 +511,8 @@ class GaussianScore(nn.Module):
             x = x.detach().requires_grad_(True)
 
             if not self.detach:
-                eps = self.sde.eps(x, t, c)
+                with input_gradient_only():
+                    eps = self.sde.eps(x, t, c)
 
             x_ = _tweedie(x, eps, mu, sigma)
 

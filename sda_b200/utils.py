@@ -110,9 +110,8 @@ def loop(
 ) -> Iterator:
     r"""Training loop generator yielding (train loss, valid loss, lr) per epoch.
 
-    Reference: sda/utils.py:89-165.  Works for the plain-PyTorch score networks (Lorenz);
-    training the libsdab U-Net needs weight gradients, a next-tier row,
-    and raises NotImplementedError from the backward pass.
+    Reference: sda/utils.py:89-165.  The libsdab U-Net trains through sdab_unet_backward
+    (tensor-core forward / input-gradient, fp32 CUDA-core weight gradients).
     """
 
     loaders = [

@@ -180,14 +180,84 @@ def test_input_gradient_adjoint_identity_at_256():
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs))
 
 
-def test_training_backward_is_a_loud_error():
+@pytest.mark.parametrize('name, size, batch', [('net_small', 16, 3), ('net_config', 32, 2)])
+def test_parameter_gradients_match_oracle(name, size, batch):
+    r"""Training path: d loss / d (every parameter) and d loss / d x of
+    the kernel with per-sample times, against torch.autograd through the fp64 oracle.  Tolerance:
+    2e-4 relative L2 per tensor (fp32 CUDA-core weight gradients over bf16x3 activations)."""
+
+    from oracle import score_oracle as so
+
+    score, k = build_score(name, size, 'cuda')
+    kern = score.kernel.train()
+    state, _ = build_state(name, size)
+    C = (2 * k + 1) * 2
+    x = randn((batch, C, size, size), seed=11)
+    t = torch.linspace(0.2, 0.9, batch)
+    r = randn((batch, C, size, size), seed=12)
+
+    ref_state = {kk: v.double().requires_grad_(v.is_floating_point() and kk != 'forcing') for kk, v in state.items()}
+    xr = x.double().requires_grad_(True)
+    ref_loss = (so.score_unet(ref_state, xr, t.double(), ref_state['forcing']) * r.double()).sum()
+    ref_loss.backward()
+
+    xg = x.cuda().requires_grad_(True)
+    loss = (kern(xg, t.cuda()) * r.cuda()).sum()
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)) + 1e-3
+    assert rel_l2(xg.grad, xr.grad) < 2e-4
+    worst = 0.0
+
+    for key, p in kern.named_parameters():
+        ref = ref_state[key].grad
+
+        if ref is None:  # embedding.freqs is a buffer in the oracle state
+            continue
+
+        assert p.grad is not None, key
+        err = rel_l2(p.grad, ref)
+        worst = max(worst, err)
+        assert err < 2e-4, f'{key}: rel-L2 {err:.2e}'
+
+    assert worst > 0.0
+
+
+def test_vpsde_loss_trains_through_the_native_unet():
+    r"""VPSDE.loss (sda/score.py:265-276) + one AdamW step (sda/utils.py:136-143) lowers the loss."""
+
     import sda_b200.score as sc
 
     score, k = build_score('net_small', 16, 'cuda')
-    sde = sc.VPSDE(score.kernel, shape=(6, 16, 16)).cuda()
+    sde = sc.VPSDE(score.kernel, shape=(6, 16, 16)).cuda().train()
+    opt = torch.optim.AdamW(sde.parameters(), lr=1e-3)
+    x = randn((8, 6, 16, 16), seed=5).cuda()
+    torch.manual_seed(0)
+    losses = []
 
-    with pytest.raises(NotImplementedError, match='input gradients only'):
-        sde.loss(torch.randn(2, 6, 16, 16, device='cuda')).backward()
+    for _ in range(12):
+        torch.manual_seed(1)  # same noise and times every step: the loss must go down
+        l = sde.loss(x)
+        opt.zero_grad()
+        l.backward()
+        opt.step()
+        losses.append(float(l))
+
+    assert all(map(lambda v: v == v, losses)) and losses[-1] < 0.9 * losses[0]
+
+
+def test_guidance_stays_on_the_input_gradient_path():
+    r"""GaussianScore differentiates w.r.t. x only although the parameters require gradients:
+    no parameter gradient may be produced (or paid for) during guided sampling."""
+
+    import sda_b200.score as sc
+
+    score, k = build_score('net_small', 16, 'cuda')
+    x = randn((1, 5, 2, 16, 16), seed=1).cuda()
+    y = randn((1, 5, 2, 8, 8), seed=2).cuda()
+    guided = sc.GaussianScore(y, A=lambda v: v[..., ::2, ::2], std=0.1, sde=sc.VPSDE(score, shape=())).cuda()
+    guided(x, torch.tensor(0.5).cuda())
+    assert score.kernel.network._saved_level == 1
+    assert all(p.grad is None for p in score.parameters())
 
 
 def test_fast_mode_error_is_reported_not_hidden(golden, monkeypatch):
