@@ -206,6 +206,9 @@ struct WgradProblem {
   float* db;        // or null
 };
 int conv3x3_wgrad(const WgradProblem& p, cudaStream_t stream);
+// tcgen05 engine (csrc/wgrad_umma.cu): g and x both as operand tensors, x_kind 0, tileable into 8 x 16 boxes
+bool wgrad_umma_supported(const WgradProblem& p);
+int conv3x3_wgrad_umma(const WgradProblem& p, int mode, cudaStream_t stream);
 // dshift[(Nt > 1 ? n : 0) * stride + c] += sum_{h, w} (a - b)[n, h, w, c]   (F(C) tensors)
 int shift_grad(const float* a, const float* b, float* dshift, int stride, int Nt, int N, int H, int W, int C,
                cudaStream_t stream);

@@ -74,6 +74,7 @@ struct Plan {
   size_t gout_op, gxf;
   std::vector<size_t> gc1op, gup, gz;
   std::vector<size_t> xs2g;  // training: the tail transposes' parity operand (xs2 itself feeds the heads' wgrad)
+  std::vector<size_t> hsave;  // training: act(conv1) of every block as operand tensor (input of conv2's wgrad)
   size_t total;
 };
 
@@ -107,13 +108,14 @@ Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save, bool 
     }
   }
   const int nblk = (int)h->block_ch.size();
-  p.aop.assign(nblk, 0), p.c1.assign(nblk, 0), p.rstd.assign(nblk, 0);
+  p.aop.assign(nblk, 0), p.c1.assign(nblk, 0), p.rstd.assign(nblk, 0), p.hsave.assign(nblk, 0);
   if (save) {
     auto per_level = [&](const std::vector<std::vector<int>>& blk) {
       for (int d = 0; d < D; ++d) {
         const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
         for (int j : blk[d]) {
           p.aop[j] = a.take(op_bytes(N, Hd, Wd, C));
+          if (train) p.hsave[j] = a.take(op_bytes(N, Hd, Wd, C));
           p.c1[j] = a.take(f_bytes(N, Hd, Wd, C));
           p.rstd[j] = a.take((size_t)N * Hd * Wd * sizeof(float));
         }
@@ -348,10 +350,11 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
                           save ? F(p.rstd[j]) : nullptr, N, Hd, Wd, C, 0, st));
     ConvProblem q{};
     q.in = aop, q.wpk = wf(c1), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = C, q.stride = 1, q.mode = mode;
-    q.epi.bias = bias(c1), q.epi.pre = save ? F(p.c1[j]) : nullptr, q.epi.act = act, q.epi.outOP = OP(p.hop[d]);
+    bf16* hop = save == 2 ? OP(p.hsave[j]) : OP(p.hop[d]);  // training keeps act(conv1) for conv2's weight gradient
+    q.epi.bias = bias(c1), q.epi.pre = save ? F(p.c1[j]) : nullptr, q.epi.act = act, q.epi.outOP = hop;
     SDAB_TRY(run_conv(engine, q, st));
     ConvProblem r{};
-    r.in = OP(p.hop[d]), r.wpk = wf(c1 + 1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
+    r.in = hop, r.wpk = wf(c1 + 1), r.N = N, r.H = Hd, r.W = Wd, r.Cin = C, r.Cout = C, r.stride = 1,
     r.mode = mode;
     r.epi.bias = bias(c1 + 1), r.epi.res = cur, r.epi.outF = dst, r.epi.outOP = dst_op;
     if (!dst_op) fuse_ln(r, next_j);
@@ -494,14 +497,15 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     w.gF = gF, w.gOP = gOP, w.xOP = xOP, w.xF = xF, w.x_kind = x_kind, w.act = act;
     w.N = N, w.H = Ho, w.W = Wo, w.Cg = Cg, w.Cx = Cx, w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin;
     w.dw = wt->dw[ci], w.db = wt->db[ci];
+    if (engine == SDAB_ENGINE_UMMA && wgrad_umma_supported(w)) return conv3x3_wgrad_umma(w, mode, st);
     return conv3x3_wgrad(w, st);
   };
 
   // backward of one block: cur (F, operand in GOP[d]) -> other ping-pong buffer (+ GOP[d])
   auto block_bwd = [&](int d, int j, int c1, const float* cur, float* dst) -> int {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
-    // conv2: output cotangent = cur, input = act(saved pre-activation)
-    SDAB_TRY(wgrad(c1 + 1, cur, nullptr, C, nullptr, F(p.c1[j]), 3, C, Hd, Wd));
+    // conv2: output cotangent = cur (operand copy in GOP[d]), input = the saved act(conv1)
+    SDAB_TRY(wgrad(c1 + 1, cur, GOP(d), C, OP(p.hsave[j]), nullptr, 0, C, Hd, Wd));
     ConvProblem q{};
     q.in = GOP(d), q.wpk = wb(c1 + 1), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = C, q.stride = 1, q.mode = mode;
     q.epi.dact = F(p.c1[j]), q.epi.dact_kind = act, q.epi.outOP = OP(p.gc1op[d]);
@@ -596,7 +600,7 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     if (d > 0)
       SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.xs2[d - 1]), nullptr, 1, h->d.hidden_channels[d - 1], Hd, Wd));
     else
-      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.in_op), nullptr, 0, round_up(h->d.in_channels, 32), Hd, Wd));
+      SDAB_TRY(wgrad(ci, cur, GOP(0), C, OP(p.in_op), nullptr, 0, round_up(h->d.in_channels, 32), Hd, Wd));
     if (d > 0 && engine == SDAB_ENGINE_UMMA) {
       // transpose of the stride-2 head by output parity: gx[2i + po, 2j + pp] only receives the taps
       // with a = po + 1 (mod 2), b = pp + 1 (mod 2) -- 1, 2, 2 and 4 taps instead of 9 on a

@@ -1,0 +1,357 @@
+// wgrad_umma.cu -- tcgen05 weight gradient of the stride-1 3x3 circular convolutions (the 36 block
+// convolutions of the U-Net, sda/nn.py:131-142): the parameter-gradient half of loss.backward() in the
+// training step (sda/utils.py:136-143).
+//
+//   dW[tap][ci][co] = sum_{pixels} x[pixel + tap][ci] * g[pixel][co]
+//
+//   GEMM view    per tap, M = 128 input channels (four 32-channel chunks), N = NBLK output channels,
+//                K = the 128 pixels of an 8 x 16 tile, accumulated over every tile of the CTA's pixel split.
+//   operands     BOTH arrive as [pixel][32 channels] tiles straight from the operand tensors (OP layout):
+//                the channels are the M / N dimension, so the descriptors are MN-major SWIZZLE_64B
+//                (leading-dimension offset = chunk stride, stride offset = 8-pixel group stride; verified by
+//                tools/probes/umma_mnmajor_probe.cu).  x is ONE haloed 10 x 18 patch per chunk: tap (a, b)
+//                shifts the descriptor start by (10 a + b) pixel rows, as in the forward patch kernel.
+//   accumulators TG taps x NBLK fp32 TMEM columns stay resident for the whole kernel; the epilogue runs once
+//                and adds the CTA's partial sums into dW (cout, cin, 3, 3) with fp32 atomics.
+//   precision    PLANES = 2: hi*hi + hi*lo + lo*hi like the forward path; PLANES = 1: bf16 single pass.
+//   schedule     one CTA per (tap group, M block, N block, pixel split); warp 0 = TMA producer, warp 1 = MMA
+//                issuer + TMEM allocator, warps 2-5 = epilogue.
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace sdab {
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBW = 8, kBH = 16;                       // pixel tile
+constexpr int kPW = kBW + 2, kPH = kBH + 2;            // haloed patch
+constexpr uint32_t kPatchBytes = kPW * kPH * 64;       // 11520 B landing per (plane, chunk)
+constexpr uint32_t kPatchSlot = 12288;                 // chunk stride of the x operand in shared memory
+constexpr uint32_t kGBytes = kBW * kBH * 64;           // 8192 B per (plane, chunk) of g
+constexpr uint32_t kSmemBudget = 227 * 1024;
+
+struct WParams {
+  int num_tiles, tiles_w, tiles_h;
+  int nchunk_x, nchunk_g;  // 32-channel chunks of the x / g tensors
+  int planes;
+  int nblk;                // output channels per CTA (multiple of 32, <= 128)
+  int tg;                  // taps per CTA
+  int ntg, nmb, nnb;       // tap groups, M blocks, N blocks
+  int splits;
+  int stages;
+  uint32_t stage_bytes, x_plane_bytes, g_plane_bytes;
+  int cin, cout;
+  float* dw;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded: a protocol bug aborts the launch instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n.reg .b32 rx;\n.reg .pred px;\nelect.sync rx|px, %1;\n@px mov.s32 %0, 1;\n}" : "+r"(pred) : "r"(0xffffffffu));
+  return pred != 0;
+}
+// MN-major SWIZZLE_64B descriptor: start address, leading-dimension offset (chunk stride), stride offset
+// (8-pixel group stride), version 1, layout type 4
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+
+template <int PLANES>
+__global__ void __launch_bounds__(kThreads, 1)
+    wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - raw);
+  const uint32_t bar_full = base, bar_empty = base + 32, bar_done = base + 64;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 96);
+  const uint32_t stage0 = base + 1024;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // work item of this CTA
+  int id = blockIdx.x;
+  const int split = id % p.splits;
+  id /= p.splits;
+  const int nb = id % p.nnb;
+  id /= p.nnb;
+  const int mb = id % p.nmb;
+  const int tgi = id / p.nmb;
+  const int tap0 = tgi * p.tg, ntap = min(p.tg, 9 - tap0);
+  const int xchunks = min(4, p.nchunk_x - 4 * mb), gchunks = p.nblk / 32;
+  const int ntiles = split < p.num_tiles ? (p.num_tiles - split + p.splits - 1) / p.splits : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 96), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    const uint32_t tx = (uint32_t)PLANES * ((uint32_t)xchunks * kPatchBytes + (uint32_t)gchunks * kGBytes);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      const int tile = split + i * p.splits;
+      const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, n = tile / (p.tiles_w * p.tiles_h);
+      const int h0 = th * kBH, w0 = tw * kBW;
+      mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+      if (elect_one()) {
+        const uint32_t full = bar_full + 8 * stage;
+        mbar_expect_tx(full, tx);
+        const uint32_t sx = stage0 + stage * p.stage_bytes, sg = sx + PLANES * p.x_plane_bytes;
+#pragma unroll
+        for (int pl = 0; pl < PLANES; ++pl) {
+          for (int c = 0; c < xchunks; ++c)
+            tma_load_5d(sx + pl * p.x_plane_bytes + c * kPatchSlot, &tmX, full, 0, w0, h0, pl * p.nchunk_x + 4 * mb + c, n);
+          for (int c = 0; c < gchunks; ++c)
+            tma_load_5d(sg + pl * p.g_plane_bytes + c * kGBytes, &tmG, full, 0, w0, h0, pl * p.nchunk_g + nb * gchunks + c, n);
+        }
+      }
+      __syncwarp();
+      if (++stage == p.stages) stage = 0, phase ^= 1;
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    // D fp32, A / B bf16, both MN-major (bits 15, 16), M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.nblk >> 3) << 17) |
+                           ((128u >> 4) << 24);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      mbar_wait(bar_full + 8 * stage, phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sx = stage0 + stage * p.stage_bytes, sg = sx + PLANES * p.x_plane_bytes;
+        for (int t = 0; t < ntap; ++t) {
+          const int tap = tap0 + t;
+          const uint32_t shift = (uint32_t)((tap / 3) * kPW + tap % 3) * 64u;
+          const uint32_t d = tmem_base + (uint32_t)(t * p.nblk);
+#pragma unroll
+          for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
+            // pass 0: hi*hi, 1: x hi * g lo, 2: x lo * g hi
+            const uint32_t xa = sx + (pass == 2 ? p.x_plane_bytes : 0u) + shift;
+            const uint32_t ga = sg + (pass == 1 ? p.g_plane_bytes : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)  // K = 16 pixels = two rows of the 8-wide tile
+              umma_bf16(d, desc_mn(xa + ks * 2 * (kPW * 64), kPatchSlot, kPW * 64), desc_mn(ga + ks * 1024, kGBytes, 512),
+                        idesc, (i | pass | ks) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar_empty + 8 * stage);
+        if (i == ntiles - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++stage == p.stages) stage = 0, phase ^= 1;
+    }
+  } else if (ntiles > 0) {
+    // ===================================================================== epilogue (warps 2..5), once
+    const int q = warp & 3;
+    const int ci = 128 * mb + q * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int t = 0; t < ntap; ++t) {
+      const int tap = tap0 + t;
+      for (int c0 = 0; c0 < p.nblk; c0 += 32) {
+        float v[32];
+        tmem_ld32(t0 + (uint32_t)(t * p.nblk + c0), v);
+        if (ci < p.cin) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = nb * p.nblk + c0 + j;
+            if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * 9 + tap, v[j]);
+          }
+        }
+      }
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// db[c] += sum over the interior pixels of an operand tensor (hi + lo)
+__global__ void op_channel_sum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int N, int H, int W, int C,
+                                      int cout, int rows_per_block) {
+  const OpShape s{N, H, W, C, 0};
+  const int c = threadIdx.x;  // blockDim.x == C
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(N * H, r0 + rows_per_block);
+  float sum = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const int n = r / H, h = r % H;
+    const bf16* row = g + op_offset(s, n, h + 1, 1) + (size_t)(c >> 5) * s.block_stride() + (c & 31);
+    for (int w = 0; w < W; ++w) sum += __bfloat162float(row[(size_t)w * 32]) + __bfloat162float(row[(size_t)w * 32 + s.lo_offset()]);
+  }
+  if (c < cout) atomicAdd(db + c, sum);
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int encode5(CUtensorMap* map, const void* ptr, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
+  auto fn = get_encode();
+  if (!fn) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled failed with code " + std::to_string(r));
+  return SDAB_OK;
+}
+
+}  // namespace
+
+bool wgrad_umma_supported(const WgradProblem& p) {
+  return p.gOP && p.xOP && p.x_kind == 0 && p.Cg % 32 == 0 && p.Cx % 32 == 0 && p.Cg >= 32 && p.Cx >= 32 &&
+         p.W % kBW == 0 && p.H % kBH == 0;
+}
+
+int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
+  SDAB_REQUIRE(wgrad_umma_supported(c) && c.dw, "unsupported weight-gradient problem for the tcgen05 engine");
+  WParams p{};
+  p.tiles_w = c.W / kBW, p.tiles_h = c.H / kBH, p.num_tiles = p.tiles_w * p.tiles_h * c.N;
+  p.nchunk_x = c.Cx / 32, p.nchunk_g = c.Cg / 32;
+  p.planes = mode == SDAB_MODE_BF16X3 ? 2 : 1;
+  p.nblk = c.Cg % 128 == 0 ? 128 : (c.Cg % 96 == 0 ? 96 : (c.Cg % 64 == 0 ? 64 : 32));
+  p.tg = 512 / p.nblk;
+  if (p.tg > 9) p.tg = 9;
+  p.ntg = (9 + p.tg - 1) / p.tg;
+  p.nmb = (p.nchunk_x + 3) / 4;
+  p.nnb = c.Cg / p.nblk;
+  p.x_plane_bytes = 4 * kPatchSlot;
+  p.g_plane_bytes = (uint32_t)(p.nblk / 32) * kGBytes;
+  p.stage_bytes = p.planes * (p.x_plane_bytes + p.g_plane_bytes);
+  p.stages = (int)((kSmemBudget - 2048) / p.stage_bytes);
+  if (p.stages > 3) p.stages = 3;
+  SDAB_REQUIRE(p.stages >= 1, "weight-gradient tile does not fit shared memory");
+  const int units = p.ntg * p.nmb * p.nnb;
+  p.splits = (2 * 148 + units - 1) / units;
+  if (p.splits > p.num_tiles) p.splits = p.num_tiles;
+  p.cin = c.cin, p.cout = c.cout, p.dw = c.dw;
+
+  CUtensorMap tmX, tmG;
+  {
+    const cuuint64_t Hp = c.H + 2, Wp = c.W + 2, Q = 2 * (cuuint64_t)p.nchunk_x;
+    const cuuint64_t dims[5] = {32, Wp, Hp, Q, (cuuint64_t)c.N};
+    const cuuint64_t strides[4] = {64, Wp * 64, Hp * Wp * 64, Q * Hp * Wp * 64};
+    const cuuint32_t box[5] = {32, kPW, kPH, 1, 1};
+    SDAB_TRY(encode5(&tmX, c.xOP, dims, strides, box));
+  }
+  {
+    // interior pixels of the haloed g operand
+    const cuuint64_t Hp = c.H + 2, Wp = c.W + 2, Q = 2 * (cuuint64_t)p.nchunk_g;
+    const bf16* basep = c.gOP + ((size_t)Wp + 1) * 32;
+    const cuuint64_t dims[5] = {32, (cuuint64_t)c.W, (cuuint64_t)c.H, Q, (cuuint64_t)c.N};
+    const cuuint64_t strides[4] = {64, Wp * 64, Hp * Wp * 64, Q * Hp * Wp * 64};
+    const cuuint32_t box[5] = {32, kBW, kBH, 1, 1};
+    SDAB_TRY(encode5(&tmG, basep, dims, strides, box));
+  }
+  const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attr_set = true;
+  }
+  const int grid = units * p.splits;
+  if (p.planes == 2)
+    wgrad_umma_kernel<2><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+  else
+    wgrad_umma_kernel<1><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+  SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
+  if (c.db) {
+    const int rows = c.N * c.H, rpb = (rows + 148 * 2 - 1) / (148 * 2);
+    op_channel_sum_kernel<<<(rows + rpb - 1) / rpb, c.Cg, 0, stream>>>(c.gOP, c.db, c.N, c.H, c.W, c.Cg, c.cout, rpb);
+    SDAB_LAUNCH_CHECK("op_channel_sum_kernel");
+  }
+  return SDAB_OK;
+}
+
+}  // namespace sdab
