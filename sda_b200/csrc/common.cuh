@@ -204,8 +204,19 @@ struct WgradProblem {
   int cout, cin;    // real channel counts
   float* dw;
   float* db;        // or null
+  // tcgen05 engine only -- generalised tap list for the strided / upsampled layers, which decompose into
+  // stride-1 sub-problems between PARITY images (the de-interleaved S2 layout) of one operand and the other
+  // operand: entry e multiplies g[pixel] with x[pixel + (tl_sa[e], tl_sb[e])] (offsets 0..2 from the patch
+  // origin) and adds the product into every weight tap of the 9-bit set tl_mask[e].  ntl == 0: the nine taps.
+  int ntl;
+  unsigned char tl_sa[9], tl_sb[9];
+  unsigned short tl_mask[9];
+  int x_par, g_par;  // 1 + parity image id ((row & 1) * 2 + (col & 1)) of an S2-layout x / g tensor, 0: normal layout
+  int g_dh, g_dw;    // origin offset of the g tile inside its parity image
 };
 int conv3x3_wgrad(const WgradProblem& p, cudaStream_t stream);
+// db[c] += sum over the pixels of an F(C) tensor, c < cout
+int f_channel_sum(const float* g, float* db, size_t pixels, int C, int cout, cudaStream_t stream);
 // tcgen05 engine (csrc/wgrad_umma.cu): g and x both as operand tensors, x_kind 0, tileable into 8 x 16 boxes
 bool wgrad_umma_supported(const WgradProblem& p);
 int conv3x3_wgrad_umma(const WgradProblem& p, int mode, cudaStream_t stream);

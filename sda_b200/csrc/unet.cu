@@ -501,6 +501,68 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     return conv3x3_wgrad(w, st);
   };
 
+  // Weight gradient of the stride-2 head ci (output cotangent g at Ho x Wo, input xs2 in the parity layout):
+  // on the tcgen05 engine, four stride-1 sub-problems by the parity (qa, qb) of the input pixel --
+  // haloed input pixel (2 o + a, 2 p + b) is pixel (o + a / 2, p + b / 2) of parity image (a & 1, b & 1).
+  auto wgrad_head = [&](int ci, const float* gF, const bf16* gOP, int C, const bf16* xs2, int Cx, int Ho, int Wo) -> int {
+    if (!wt) return SDAB_OK;
+    WgradProblem w{};
+    w.gF = gF, w.gOP = gOP, w.xOP = xs2, w.x_kind = 0, w.act = act, w.N = N, w.H = Ho, w.W = Wo, w.Cg = C, w.Cx = Cx;
+    w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin, w.dw = wt->dw[ci], w.db = wt->db[ci];
+    if (engine == SDAB_ENGINE_UMMA && wgrad_umma_supported(w)) {
+      for (int qa = 0; qa < 2; ++qa)
+        for (int qb = 0; qb < 2; ++qb) {
+          WgradProblem s = w;
+          s.x_par = 1 + qa * 2 + qb, s.db = (qa | qb) ? nullptr : w.db;
+          for (int sa = 0; sa < (qa ? 1 : 2); ++sa)
+            for (int sb = 0; sb < (qb ? 1 : 2); ++sb) {
+              s.tl_sa[s.ntl] = (unsigned char)sa, s.tl_sb[s.ntl] = (unsigned char)sb;
+              s.tl_mask[s.ntl++] = (unsigned short)(1u << (3 * (2 * sa + qa) + 2 * sb + qb));
+            }
+          SDAB_TRY(conv3x3_wgrad_umma(s, mode, st));
+        }
+      return SDAB_OK;
+    }
+    w.x_kind = 1;
+    return conv3x3_wgrad(w, st);
+  };
+  // Weight gradient of the tail ci = LN -> nearest x2 -> conv (output cotangent at 2 Hl x 2 Wl: gF, and in the
+  // parity layout gS2; input xlo at Hl x Wl): four stride-1 sub-problems by the output parity (po, pp) --
+  // output pixel (2 i + po, 2 j + pp) reads xlo[i + floor((po + a - 1) / 2), j + floor((pp + b - 1) / 2)] for
+  // tap (a, b), so each low-resolution offset collects one or two taps per axis.
+  auto wgrad_tail = [&](int ci, const float* gF, const bf16* gS2, int C, const bf16* xlo, int Cx, int Hl, int Wl) -> int {
+    if (!wt) return SDAB_OK;
+    WgradProblem w{};
+    w.gF = gF, w.gOP = gS2, w.xOP = xlo, w.x_kind = 0, w.act = act, w.N = N, w.H = Hl, w.W = Wl, w.Cg = C, w.Cx = Cx;
+    w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin, w.dw = wt->dw[ci], w.db = nullptr;
+    if (engine == SDAB_ENGINE_UMMA && gS2 && wgrad_umma_supported(w)) {
+      SDAB_TRY(f_channel_sum(gF, wt->db[ci], (size_t)N * 4 * Hl * Wl, C, w.cout, st));
+      for (int po = 0; po < 2; ++po)
+        for (int pp = 0; pp < 2; ++pp) {
+          WgradProblem s = w;
+          s.g_par = 1 + ((po + 1) & 1) * 2 + ((pp + 1) & 1), s.g_dh = (po + 1) >> 1, s.g_dw = (pp + 1) >> 1;
+          for (int da = po - 1; da <= po; ++da)
+            for (int db = pp - 1; db <= pp; ++db) {
+              unsigned mask = 0;
+              for (int a = 0; a < 3; ++a)
+                for (int b = 0; b < 3; ++b) {
+                  const int fa = (po + a - 1) >= 0 ? (po + a - 1) / 2 : -1, fb = (pp + b - 1) >= 0 ? (pp + b - 1) / 2 : -1;
+                  if (fa == da && fb == db) mask |= 1u << (3 * a + b);
+                }
+              s.tl_sa[s.ntl] = (unsigned char)(da + 1), s.tl_sb[s.ntl] = (unsigned char)(db + 1);
+              s.tl_mask[s.ntl++] = (unsigned short)mask;
+            }
+          SDAB_TRY(conv3x3_wgrad_umma(s, mode, st));
+        }
+      return SDAB_OK;
+    }
+    // CUDA-core path: the upsample is folded into the operand loader (the SIMT engine's tail input is
+    // already at the high resolution)
+    w.gOP = nullptr, w.H = 2 * Hl, w.W = 2 * Wl, w.db = wt->db[ci];
+    w.x_kind = engine == SDAB_ENGINE_UMMA ? 2 : 0;
+    return conv3x3_wgrad(w, st);
+  };
+
   // backward of one block: cur (F, operand in GOP[d]) -> other ping-pong buffer (+ GOP[d])
   auto block_bwd = [&](int d, int j, int c1, const float* cur, float* dst) -> int {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
@@ -558,8 +620,8 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
       const int ci = h->tail_conv[d + 1];
       const int Cn = h->d.hidden_channels[d + 1];
       // tail conv: output cotangent = cur, input = nearest x2 of the saved low-resolution LayerNorm output
-      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.upop[d + 1]), nullptr, 2, Cn, Hd, Wd));
       SDAB_TRY(f_to_operand(cur, OP(p.xs2g[d]), N, Hd, Wd, C, 1, st));
+      SDAB_TRY(wgrad_tail(ci, cur, OP(p.xs2g[d]), C, OP(p.upop[d + 1]), Cn, Hd / 2, Wd / 2));
       ConvProblem q{};
       q.in = OP(p.xs2g[d]), q.in_s2 = 1, q.wpk = (const bf16*)(pk + h->convs[ci].off_tb), q.wtaps = 16;
       q.N = N, q.H = Hd / 2, q.W = Wd / 2, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
@@ -577,7 +639,7 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
       gskip[d] = cur;
       const int ci = h->tail_conv[d + 1];
       const int Cn = h->d.hidden_channels[d + 1];
-      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.upop[d + 1]), nullptr, 0, Cn, Hd, Wd));
+      SDAB_TRY(wgrad_tail(ci, cur, nullptr, C, OP(p.upop[d + 1]), Cn, Hd / 2, Wd / 2));
       ConvProblem q{};
       q.in = GOP(d), q.wpk = wb(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
       q.epi.outF = F(p.gup[d + 1]);
@@ -598,7 +660,7 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     // head conv: output cotangent = cur; input = the level below in the parity layout (stride 2), or the
     // packed network input
     if (d > 0)
-      SDAB_TRY(wgrad(ci, cur, nullptr, C, OP(p.xs2[d - 1]), nullptr, 1, h->d.hidden_channels[d - 1], Hd, Wd));
+      SDAB_TRY(wgrad_head(ci, cur, GOP(d), C, OP(p.xs2[d - 1]), h->d.hidden_channels[d - 1], Hd, Wd));
     else
       SDAB_TRY(wgrad(ci, cur, GOP(0), C, OP(p.in_op), nullptr, 0, round_up(h->d.in_channels, 32), Hd, Wd));
     if (d > 0 && engine == SDAB_ENGINE_UMMA) {

@@ -131,7 +131,25 @@ __global__ void shift_grad_kernel(const float* __restrict__ a, const float* __re
   }
 }
 
+// db[c] += sum over all pixels of an F(C) tensor
+__global__ void f_channel_sum_kernel(const float* __restrict__ g, float* __restrict__ db, size_t pixels, int C, int cout,
+                                     size_t per) {
+  const size_t p0 = (size_t)blockIdx.x * per, p1 = p0 + per < pixels ? p0 + per : pixels;
+  for (int c = threadIdx.x; c < cout; c += blockDim.x) {
+    float s = 0.f;
+    for (size_t px = p0; px < p1; ++px) s += g[px * C + c];
+    atomicAdd(db + c, s);
+  }
+}
+
 }  // namespace
+
+int f_channel_sum(const float* g, float* db, size_t pixels, int C, int cout, cudaStream_t st) {
+  const size_t blocks = pixels < 148 * 4 ? pixels : 148 * 4, per = (pixels + blocks - 1) / blocks;
+  f_channel_sum_kernel<<<(unsigned)((pixels + per - 1) / per), 128, 0, st>>>(g, db, pixels, C, cout, per);
+  SDAB_LAUNCH_CHECK("f_channel_sum_kernel");
+  return SDAB_OK;
+}
 
 int conv3x3_wgrad(const WgradProblem& p, cudaStream_t st) {
   SDAB_REQUIRE(p.dw && (p.gF || p.gOP) && (p.xOP || p.xF), "null argument");

@@ -46,6 +46,10 @@ struct WParams {
   uint32_t stage_bytes, x_plane_bytes, g_plane_bytes;
   int cin, cout;
   float* dw;
+  int ntl;                 // tap-list entries
+  uint32_t tl_shift[9];    // patch-row shift of entry e (pixels)
+  uint32_t tl_mask[9];     // weight taps entry e adds into
+  int x_par, g_par, g_dh, g_dw;  // parity-image selection (WgradProblem)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   id /= p.nnb;
   const int mb = id % p.nmb;
   const int tgi = id / p.nmb;
-  const int tap0 = tgi * p.tg, ntap = min(p.tg, 9 - tap0);
+  const int tap0 = tgi * p.tg, ntap = min(p.tg, p.ntl - tap0);  // entries of the tap list handled here
   const int xchunks = min(4, p.nchunk_x - 4 * mb), gchunks = p.nblk / 32;
   const int ntiles = split < p.num_tiles ? (p.num_tiles - split + p.splits - 1) / p.splits : 0;
 
@@ -175,10 +179,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         const uint32_t sx = stage0 + stage * p.stage_bytes, sg = sx + PLANES * p.x_plane_bytes;
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl) {
-          for (int c = 0; c < xchunks; ++c)
-            tma_load_5d(sx + pl * p.x_plane_bytes + c * kPatchSlot, &tmX, full, 0, w0, h0, pl * p.nchunk_x + 4 * mb + c, n);
-          for (int c = 0; c < gchunks; ++c)
-            tma_load_5d(sg + pl * p.g_plane_bytes + c * kGBytes, &tmG, full, 0, w0, h0, pl * p.nchunk_g + nb * gchunks + c, n);
+          for (int c = 0; c < xchunks; ++c) {
+            const int q = pl * p.nchunk_x + 4 * mb + c;
+            tma_load_5d(sx + pl * p.x_plane_bytes + c * kPatchSlot, &tmX, full, 0, w0, h0, p.x_par ? 4 * q + p.x_par - 1 : q, n);
+          }
+          for (int c = 0; c < gchunks; ++c) {
+            const int q = pl * p.nchunk_g + nb * gchunks + c;
+            tma_load_5d(sg + pl * p.g_plane_bytes + c * kGBytes, &tmG, full, 0, w0 + p.g_dw, h0 + p.g_dh,
+                        p.g_par ? 4 * q + p.g_par - 1 : q, n);
+          }
         }
       }
       __syncwarp();
@@ -197,8 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (elect_one()) {
         const uint32_t sx = stage0 + stage * p.stage_bytes, sg = sx + PLANES * p.x_plane_bytes;
         for (int t = 0; t < ntap; ++t) {
-          const int tap = tap0 + t;
-          const uint32_t shift = (uint32_t)((tap / 3) * kPW + tap % 3) * 64u;
+          const uint32_t shift = p.tl_shift[tap0 + t] * 64u;
           const uint32_t d = tmem_base + (uint32_t)(t * p.nblk);
 #pragma unroll
           for (int pass = 0; pass < (PLANES == 2 ? 3 : 1); ++pass) {
@@ -225,15 +233,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < ntap; ++t) {
-      const int tap = tap0 + t;
+      const uint32_t mask = p.tl_mask[tap0 + t];
       for (int c0 = 0; c0 < p.nblk; c0 += 32) {
         float v[32];
         tmem_ld32(t0 + (uint32_t)(t * p.nblk + c0), v);
         if (ci < p.cin) {
+          for (int tap = 0; tap < 9; ++tap) {
+            if (!(mask >> tap & 1u)) continue;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int co = nb * p.nblk + c0 + j;
-            if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * 9 + tap, v[j]);
+            for (int j = 0; j < 32; ++j) {
+              const int co = nb * p.nblk + c0 + j;
+              if (co < p.cout) atomicAdd(p.dw + ((size_t)co * p.cin + ci) * 9 + tap, v[j]);
+            }
           }
         }
       }
@@ -288,9 +299,10 @@ int encode5(CUtensorMap* map, const void* ptr, const cuuint64_t* dims, const cuu
 
 }  // namespace
 
+// H, W: resolution of the (sub-)problem, i.e. of the pixel tiles shared by the g and x tiles
 bool wgrad_umma_supported(const WgradProblem& p) {
   return p.gOP && p.xOP && p.x_kind == 0 && p.Cg % 32 == 0 && p.Cx % 32 == 0 && p.Cg >= 32 && p.Cx >= 32 &&
-         p.W % kBW == 0 && p.H % kBH == 0;
+         p.W % kBW == 0 && p.H % kBH == 0 && p.ntl >= 0 && p.ntl <= 9;
 }
 
 int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
@@ -300,9 +312,21 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   p.nchunk_x = c.Cx / 32, p.nchunk_g = c.Cg / 32;
   p.planes = mode == SDAB_MODE_BF16X3 ? 2 : 1;
   p.nblk = c.Cg % 128 == 0 ? 128 : (c.Cg % 96 == 0 ? 96 : (c.Cg % 64 == 0 ? 64 : 32));
+  if (c.ntl) {
+    p.ntl = c.ntl;
+    for (int e = 0; e < c.ntl; ++e) {
+      SDAB_REQUIRE(c.tl_sa[e] <= 2 && c.tl_sb[e] <= 2 && c.tl_mask[e] < 512, "invalid tap list");
+      p.tl_shift[e] = (uint32_t)c.tl_sa[e] * kPW + c.tl_sb[e], p.tl_mask[e] = c.tl_mask[e];
+    }
+  } else {
+    p.ntl = 9;
+    for (int e = 0; e < 9; ++e) p.tl_shift[e] = (uint32_t)(e / 3) * kPW + e % 3, p.tl_mask[e] = 1u << e;
+  }
+  p.x_par = c.x_par, p.g_par = c.g_par, p.g_dh = c.g_dh, p.g_dw = c.g_dw;
+  SDAB_REQUIRE(p.x_par >= 0 && p.x_par <= 4 && p.g_par >= 0 && p.g_par <= 4, "invalid parity image");
   p.tg = 512 / p.nblk;
-  if (p.tg > 9) p.tg = 9;
-  p.ntg = (9 + p.tg - 1) / p.tg;
+  if (p.tg > p.ntl) p.tg = p.ntl;
+  p.ntg = (p.ntl + p.tg - 1) / p.tg;
   p.nmb = (p.nchunk_x + 3) / 4;
   p.nnb = c.Cg / p.nblk;
   p.x_plane_bytes = 4 * kPatchSlot;
@@ -317,22 +341,30 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   p.cin = c.cin, p.cout = c.cout, p.dw = c.dw;
 
   CUtensorMap tmX, tmG;
-  {
-    const cuuint64_t Hp = c.H + 2, Wp = c.W + 2, Q = 2 * (cuuint64_t)p.nchunk_x;
+  // A tensor in the S2 layout holds an image of twice the sub-problem resolution as four parity images of
+  // (H + 1) x (W + 1) haloed pixels; dim 3 then indexes (plane, chunk, parity).  Boxes that stick out of a
+  // parity image read zeros, which only meet pixels outside the tile.
+  auto make_map = [&](CUtensorMap* map, const bf16* ptr, int nchunk, int par, bool interior, int bw, int bh) -> int {
+    const cuuint64_t Q = 2 * (cuuint64_t)nchunk;
+    if (par) {
+      const cuuint64_t Hp = 2 * c.H + 2, Wp = 2 * c.W + 2;
+      const cuuint64_t dims[5] = {32, Wp / 2, Hp / 2, 4 * Q, (cuuint64_t)c.N};
+      const cuuint64_t strides[4] = {64, (Wp / 2) * 64, (Hp / 2) * (Wp / 2) * 64, Q * Hp * Wp * 64};
+      const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+      return encode5(map, ptr, dims, strides, box);
+    }
+    const cuuint64_t Hp = c.H + 2, Wp = c.W + 2;
+    const cuuint64_t strides[4] = {64, Wp * 64, Hp * Wp * 64, Q * Hp * Wp * 64};
+    const cuuint32_t box[5] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1, 1};
+    if (interior) {  // tiles of the interior pixels of a haloed operand
+      const cuuint64_t dims[5] = {32, (cuuint64_t)c.W, (cuuint64_t)c.H, Q, (cuuint64_t)c.N};
+      return encode5(map, ptr + ((size_t)Wp + 1) * 32, dims, strides, box);
+    }
     const cuuint64_t dims[5] = {32, Wp, Hp, Q, (cuuint64_t)c.N};
-    const cuuint64_t strides[4] = {64, Wp * 64, Hp * Wp * 64, Q * Hp * Wp * 64};
-    const cuuint32_t box[5] = {32, kPW, kPH, 1, 1};
-    SDAB_TRY(encode5(&tmX, c.xOP, dims, strides, box));
-  }
-  {
-    // interior pixels of the haloed g operand
-    const cuuint64_t Hp = c.H + 2, Wp = c.W + 2, Q = 2 * (cuuint64_t)p.nchunk_g;
-    const bf16* basep = c.gOP + ((size_t)Wp + 1) * 32;
-    const cuuint64_t dims[5] = {32, (cuuint64_t)c.W, (cuuint64_t)c.H, Q, (cuuint64_t)c.N};
-    const cuuint64_t strides[4] = {64, Wp * 64, Hp * Wp * 64, Q * Hp * Wp * 64};
-    const cuuint32_t box[5] = {32, kBW, kBH, 1, 1};
-    SDAB_TRY(encode5(&tmG, basep, dims, strides, box));
-  }
+    return encode5(map, ptr, dims, strides, box);
+  };
+  SDAB_TRY(make_map(&tmX, c.xOP, p.nchunk_x, p.x_par, false, kPW, kPH));
+  SDAB_TRY(make_map(&tmG, c.gOP, p.nchunk_g, p.g_par, true, kBW, kBH));
   const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {

@@ -180,7 +180,7 @@ def test_input_gradient_adjoint_identity_at_256():
     assert abs(lhs - rhs) <= 2e-3 * max(abs(lhs), abs(rhs))
 
 
-@pytest.mark.parametrize('name, size, batch', [('net_small', 16, 3), ('net_config', 32, 2)])
+@pytest.mark.parametrize('name, size, batch', [('net_small', 16, 3), ('net_config', 32, 2), ('net_config', 64, 1)])
 def test_parameter_gradients_match_oracle(name, size, batch):
     r"""Training path: d loss / d (every parameter) and d loss / d x of
     the kernel with per-sample times, against torch.autograd through the fp64 oracle.  Tolerance:
