@@ -40,6 +40,8 @@ import torch  # noqa: E402
 WINDOW, CHANNELS, BLOCKS = 5, (96, 192, 384), (3, 3, 3)
 SIZE, LENGTH = 256, 64
 SCHEDULE_STEPS, CORRECTIONS, TAU = 256, 1, 0.5
+VARIANTS = {'guided': 'guided (GaussianScore, detach=False)', 'detach': 'guided without back-propagation (GaussianScore, detach=True)',
+            'unguided': 'unguided (eps = MCScoreNet)'}
 CONV_FLOP_PER_PIXEL = 6_837_696  # forward conv FLOPs per output pixel and window
 
 
@@ -178,7 +180,7 @@ def run_reference(args, rank):
 def workload_config(args, world):
     return {
         'workload': f'Kolmogorov {SIZE}x{SIZE}, L={LENGTH}, B={args.batch}, window {WINDOW} (k=2) -> {args.batch * (LENGTH - 4)} windows; '
-                    f'U-Net {CHANNELS} x {BLOCKS}; guided (GaussianScore, detach=False), corrections={CORRECTIONS}, tau={TAU}',
+                    f'U-Net {CHANNELS} x {BLOCKS}; {VARIANTS[args.variant]}, corrections={CORRECTIONS}, tau={TAU}',
         'windows': args.batch * (LENGTH - 4),
         'score_evaluations_per_step': 1 + CORRECTIONS,
         'parallelism': f'window-sharded x{world}' if world > 1 else 'single GPU',
@@ -211,8 +213,16 @@ def run_ours(args, rank, local_rank, world):
 
     x_host, y_host = synthetic(args.batch, LENGTH, SIZE)
     x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
-    guided = sc.GaussianScore(y_host.to(device), A=observation, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2).to(device)
-    sde = sc.VPSDE(guided, shape=tuple(x_host.shape[1:])).to(device)
+    # --variant: guided (the metric: GaussianScore, forward + input-gradient), detach (GaussianScore(detach=True),
+    # score.py:378-379: no back-propagation through the network) or unguided (eps = MCScoreNet, prior sampling)
+    guided = None
+
+    if args.variant == 'unguided':
+        sde = sc.VPSDE(score, shape=tuple(x_host.shape[1:])).to(device)
+    else:
+        guided = sc.GaussianScore(y_host.to(device), A=observation, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2,
+                                  detach=args.variant == 'detach').to(device)
+        sde = sc.VPSDE(guided, shape=tuple(x_host.shape[1:])).to(device)
     x = x_host.to(device)
     state = sde.sampler_state(x, SCHEDULE_STEPS)
 
@@ -266,7 +276,8 @@ def run_ours(args, rank, local_rank, world):
 
     for _ in range(args.steps):
         x.copy_(x_pin, non_blocking=True)
-        guided.y.copy_(y_pin, non_blocking=True)
+        if guided is not None:
+            guided.y.copy_(y_pin, non_blocking=True)
         x = sde.denoise_step(x, step % SCHEDULE_STEPS, state, corrections=CORRECTIONS, tau=TAU)
         x_pin.copy_(x, non_blocking=True)
         torch.cuda.synchronize()
@@ -317,7 +328,7 @@ def run_ours(args, rank, local_rank, world):
         },
     }
 
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.variant == 'guided':
         sec, cores = cpu_step_seconds(2, 0)
         windows = LENGTH - 2 * (WINDOW // 2)
         out['cpu_baseline'] = {
@@ -340,6 +351,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1, help='trajectories sampled together (B)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--variant', default='guided', choices=sorted(VARIANTS),
+                    help='guided is the BASELINE metric; the others are reported beside it (SURVEY.md section 8d)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
