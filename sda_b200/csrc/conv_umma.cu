@@ -49,7 +49,7 @@ constexpr int kPatchW = kPatchBW + 2, kPatchH = kPatchBH + 2;
 constexpr uint32_t kPatchBytes = kPatchW * kPatchH * 64;  // 11520 B landing per (plane, K-block)
 constexpr uint32_t kPatchPlane = 12288;                   // padded to the 1 KB swizzle alignment
 constexpr uint32_t kPatchSBO = kPatchW * 64;
-constexpr int kMaxBStages = 16, kMaxAStages = 4;
+constexpr int kMaxBStages = 16;  // (the control block has room for 4 patch stages)
 
 struct UmmaParams {
   TileGeom g;
@@ -213,11 +213,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
-               "r"(c0), "r"(c1)
-               : "memory");
-}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1), "r"(c2)
@@ -231,16 +226,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
 }
 // named barrier of one epilogue warpgroup (ids 1 and 2; 0 is __syncthreads)
 __device__ __forceinline__ void epi_barrier(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
@@ -326,11 +311,6 @@ __device__ __forceinline__ void load32_hilo(const bf16* __restrict__ hi, const b
   }
 }
 
-// K-major, SWIZZLE_64B shared-memory matrix descriptor: 8-row groups of 64 B rows, 512 B apart.
-__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
-}
 
 // ------------------------------------------------------------------------------------------ epilogue
 // Epilogue role (warps 2..5 of both kernels): TMEM -> registers -> fused bias / residual / activation /

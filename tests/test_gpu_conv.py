@@ -90,3 +90,34 @@ def test_unsupported_shapes_are_explicit_errors():
 
     with pytest.raises(RuntimeError, match='power of two'):
         run(x, w, None, 1, 0, 0, 0)
+
+
+def test_patch_kernel_agrees_with_per_tap_kernel():
+    r"""The patch kernel (one haloed input patch per K-block, taps as shifted descriptors, K-block-major
+    accumulation) against the per-tap kernel (SDAB_UMMA_PATCH=0, read once at library load, hence a
+    subprocess): same products, different summation order."""
+
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    code = """
+import os, sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from test_gpu_conv import run
+torch.manual_seed(3)
+x = torch.randn(2, 192, 32, 64, device='cuda'); w = torch.randn(192, 192, 3, 3, device='cuda') / (9 * 192) ** 0.5
+b = torch.randn(192, device='cuda')
+torch.save(run(x, w, b, 1, 0, 0, 0).cpu(), sys.argv[1])
+"""
+    root = Path(__file__).resolve().parents[1]
+    outs = []
+
+    for flag in ('1', '0'):
+        path = root / f'.pytest_patch_{flag}.pt'
+        env = dict(**__import__('os').environ, SDAB_UMMA_PATCH=flag)
+        subprocess.run([sys.executable, '-c', code.format(root=str(root), tests=str(root / 'tests')), str(path)], check=True, env=env, timeout=300)
+        outs.append(torch.load(path))
+        path.unlink()
+
+    assert rel_l2(outs[0], outs[1]) < 5e-6

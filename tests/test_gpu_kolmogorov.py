@@ -13,7 +13,7 @@ from oracle import kolmogorov_oracle as ko
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('size', [64, 256])
+@pytest.mark.parametrize('size', [64, 128, 256])  # 64 / 256: fused radix-8 / radix-16 path, 128: generic 5-kernel path
 def test_transition_matches_oracle(size):
     from sda_b200.mcs import KolmogorovFlow
 

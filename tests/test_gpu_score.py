@@ -204,7 +204,7 @@ def test_parameter_gradients_match_oracle(name, size, batch):
     xg = x.cuda().requires_grad_(True)
     loss = (kern(xg, t.cuda()) * r.cuda()).sum()
     loss.backward()
-    assert abs(float(loss) - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)) + 1e-3
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) <= 1e-4 * abs(float(ref_loss.detach())) + 1e-3
     assert rel_l2(xg.grad, xr.grad) < 2e-4
     worst = 0.0
 

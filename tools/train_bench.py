@@ -100,7 +100,7 @@ def main():
             'ms_per_iteration': ms / iters, 'iterations_per_s': iters / (ms * 1e-3),
             'samples_per_s': 32 * world * iters / (ms * 1e-3),
             'algorithmic_tflops': 3 * 32 * world * bench.CONV_FLOP_PER_PIXEL * 64 * 64 * iters / (ms * 1e-3) / 1e12,
-            'gpu_launches_per_iteration': _lib.launch_count() / iters, 'loss': float(loss),
+            'gpu_launches_per_iteration': _lib.launch_count() / iters, 'loss': float(loss.detach()),
         }))
 
     if world > 1:
