@@ -18,6 +18,7 @@
 //                issuer + TMEM allocator, warps 2-5 = epilogue.
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -336,7 +337,9 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   if (p.stages > 3) p.stages = 3;
   SDAB_REQUIRE(p.stages >= 1, "weight-gradient tile does not fit shared memory");
   const int units = p.ntg * p.nmb * p.nnb;
-  p.splits = (2 * 148 + units - 1) / units;
+  // one wave of CTAs: every extra pixel split repeats the epilogue's atomics over the whole gradient
+  static const int waves_x2 = getenv("SDAB_WGRAD_WAVES_X2") ? atoi(getenv("SDAB_WGRAD_WAVES_X2")) : 2;
+  p.splits = (waves_x2 * 74 + units - 1) / units;
   if (p.splits > p.num_tiles) p.splits = p.num_tiles;
   p.cin = c.cin, p.cout = c.cout, p.dw = c.dw;
 
@@ -379,7 +382,7 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
     wgrad_umma_kernel<1><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
   if (c.db) {
-    const int rows = c.N * c.H, rpb = (rows + 148 * 2 - 1) / (148 * 2);
+    const int rows = c.N * c.H, rpb = (rows + 148 * 16 - 1) / (148 * 16);
     op_channel_sum_kernel<<<(rows + rpb - 1) / rpb, c.Cg, 0, stream>>>(c.gOP, c.db, c.N, c.H, c.W, c.Cg, c.cout, rpb);
     SDAB_LAUNCH_CHECK("op_channel_sum_kernel");
   }
