@@ -5,11 +5,12 @@
 //   dW[tap][ci][co] = sum_{pixels} x[pixel + tap][ci] * g[pixel][co]
 //
 //   GEMM view    per tap, M = 128 input channels (four 32-channel chunks), N = NBLK output channels,
-//                K = the 128 pixels of an 8 x 16 tile, accumulated over every tile of the CTA's pixel split.
+//                K = the pixels of an 8 x 16 (bf16) or 8 x 8 (bf16x3) tile, accumulated over every tile of the
+//                CTA's pixel split.
 //   operands     BOTH arrive as [pixel][32 channels] tiles straight from the operand tensors (OP layout):
 //                the channels are the M / N dimension, so the descriptors are MN-major SWIZZLE_64B
 //                (leading-dimension offset = chunk stride, stride offset = 8-pixel group stride; verified by
-//                tools/probes/umma_mnmajor_probe.cu).  x is ONE haloed 10 x 18 patch per chunk: tap (a, b)
+//                tools/probes/umma_mnmajor_probe.cu).  x is ONE haloed 10 x (BH + 2) patch per chunk: tap (a, b)
 //                shifts the descriptor start by (10 a + b) pixel rows, as in the forward patch kernel.
 //   accumulators TG taps x NBLK fp32 TMEM columns stay resident for the whole kernel; the epilogue runs once
 //                and adds the CTA's partial sums into dW (cout, cin, 3, 3) with fp32 atomics.
@@ -28,11 +29,16 @@ namespace sdab {
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kBW = 8, kBH = 16;                       // pixel tile
-constexpr int kPW = kBW + 2, kPH = kBH + 2;            // haloed patch
-constexpr uint32_t kPatchBytes = kPW * kPH * 64;       // 11520 B landing per (plane, chunk)
-constexpr uint32_t kPatchSlot = 12288;                 // chunk stride of the x operand in shared memory
-constexpr uint32_t kGBytes = kBW * kBH * 64;           // 8192 B per (plane, chunk) of g
+// Pixel tile: 8 x BH pixels, BH = 16 (K = 128 per tile) or 8 (K = 64: half-size stages, so that the two
+// planes of the bf16x3 mode still leave room for a second pipeline stage).
+constexpr int kBW = 8, kPW = kBW + 2;
+template <int BH>
+struct Tile {
+  static constexpr int kPH = BH + 2;                                        // haloed patch rows
+  static constexpr uint32_t kPatchBytes = kPW * kPH * 64;                   // landing per (plane, chunk) of x
+  static constexpr uint32_t kPatchSlot = (kPatchBytes + 1023u) & ~1023u;    // chunk stride of x in shared memory
+  static constexpr uint32_t kGBytes = kBW * BH * 64;                        // per (plane, chunk) of g
+};
 constexpr uint32_t kSmemBudget = 227 * 1024;
 
 struct WParams {
@@ -122,9 +128,11 @@ __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo, uint32_
          ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
 }
 
-template <int PLANES>
+template <int PLANES, int BH>
 __global__ void __launch_bounds__(kThreads, 1)
     wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG, const WParams p) {
+  constexpr uint32_t kPatchBytes = Tile<BH>::kPatchBytes, kPatchSlot = Tile<BH>::kPatchSlot, kGBytes = Tile<BH>::kGBytes;
+  constexpr int kBH = BH;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             const uint32_t xa = sx + (pass == 2 ? p.x_plane_bytes : 0u) + shift;
             const uint32_t ga = sg + (pass == 1 ? p.g_plane_bytes : 0u);
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks)  // K = 16 pixels = two rows of the 8-wide tile
+            for (int ks = 0; ks < BH / 2; ++ks)  // K = 16 pixels = two rows of the 8-wide tile
               umma_bf16(d, desc_mn(xa + ks * 2 * (kPW * 64), kPatchSlot, kPW * 64), desc_mn(ga + ks * 1024, kGBytes, 512),
                         idesc, (i | pass | ks) ? 1u : 0u);
           }
@@ -303,15 +311,18 @@ int encode5(CUtensorMap* map, const void* ptr, const cuuint64_t* dims, const cuu
 // H, W: resolution of the (sub-)problem, i.e. of the pixel tiles shared by the g and x tiles
 bool wgrad_umma_supported(const WgradProblem& p) {
   return p.gOP && p.xOP && p.x_kind == 0 && p.Cg % 32 == 0 && p.Cx % 32 == 0 && p.Cg >= 32 && p.Cx >= 32 &&
-         p.W % kBW == 0 && p.H % kBH == 0 && p.ntl >= 0 && p.ntl <= 9;
+         p.W % kBW == 0 && p.H % 16 == 0 && p.ntl >= 0 && p.ntl <= 9;
 }
 
 int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   SDAB_REQUIRE(wgrad_umma_supported(c) && c.dw, "unsupported weight-gradient problem for the tcgen05 engine");
   WParams p{};
-  p.tiles_w = c.W / kBW, p.tiles_h = c.H / kBH, p.num_tiles = p.tiles_w * p.tiles_h * c.N;
-  p.nchunk_x = c.Cx / 32, p.nchunk_g = c.Cg / 32;
   p.planes = mode == SDAB_MODE_BF16X3 ? 2 : 1;
+  const int BH = p.planes == 2 ? 8 : 16;
+  const uint32_t kPatchSlot = BH == 8 ? Tile<8>::kPatchSlot : Tile<16>::kPatchSlot;
+  const uint32_t kGBytes = BH == 8 ? Tile<8>::kGBytes : Tile<16>::kGBytes;
+  p.tiles_w = c.W / kBW, p.tiles_h = c.H / BH, p.num_tiles = p.tiles_w * p.tiles_h * c.N;
+  p.nchunk_x = c.Cx / 32, p.nchunk_g = c.Cg / 32;
   p.nblk = c.Cg % 128 == 0 ? 128 : (c.Cg % 96 == 0 ? 96 : (c.Cg % 64 == 0 ? 64 : 32));
   if (c.ntl) {
     p.ntl = c.ntl;
@@ -366,20 +377,20 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
     const cuuint64_t dims[5] = {32, Wp, Hp, Q, (cuuint64_t)c.N};
     return encode5(map, ptr, dims, strides, box);
   };
-  SDAB_TRY(make_map(&tmX, c.xOP, p.nchunk_x, p.x_par, false, kPW, kPH));
-  SDAB_TRY(make_map(&tmG, c.gOP, p.nchunk_g, p.g_par, true, kBW, kBH));
+  SDAB_TRY(make_map(&tmX, c.xOP, p.nchunk_x, p.x_par, false, kPW, BH + 2));
+  SDAB_TRY(make_map(&tmG, c.gOP, p.nchunk_g, p.g_par, true, kBW, BH));
   const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
-    SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attr_set = true;
   }
   const int grid = units * p.splits;
   if (p.planes == 2)
-    wgrad_umma_kernel<2><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+    wgrad_umma_kernel<2, 8><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   else
-    wgrad_umma_kernel<1><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+    wgrad_umma_kernel<1, 16><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
   if (c.db) {
     const int rows = c.N * c.H, rpb = (rows + 148 * 16 - 1) / (148 * 16);

@@ -222,6 +222,28 @@ def test_parameter_gradients_match_oracle(name, size, batch):
     assert worst > 0.0
 
 
+def test_parameter_gradients_on_the_cuda_core_engine(monkeypatch):
+    r"""SDAB_ENGINE=simt: fp32 CUDA-core convolutions AND weight gradients (every operand loader of
+    csrc/wgrad.cu: stride-2 parity layout, tails at the high resolution) against the tensor-core engine,
+    with a scalar time (one shared shift row)."""
+
+    score, k = build_score('net_small', 16, 'cuda')
+    kern = score.kernel.train()
+    x = randn((2, 6, 16, 16), seed=21).cuda()
+    r = randn((2, 6, 16, 16), seed=22).cuda()
+    t = torch.tensor(0.4, device='cuda')
+    grads = {}
+
+    for engine in ('umma', 'simt'):
+        monkeypatch.setenv('SDAB_ENGINE', engine)
+        kern.zero_grad()
+        (kern(x, t) * r).sum().backward()
+        grads[engine] = {key: p.grad.clone() for key, p in kern.named_parameters()}
+
+    for key in grads['umma']:
+        assert rel_l2(grads['simt'][key], grads['umma'][key]) < 1e-4, key
+
+
 def test_vpsde_loss_trains_through_the_native_unet():
     r"""VPSDE.loss (sda/score.py:265-276) + one AdamW step (sda/utils.py:136-143) lowers the loss."""
 
