@@ -82,6 +82,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 22)) __trap();
   }
 }
+// the epilogue's single wait spans the CTA's whole main loop: same idea, a bound of seconds
+__device__ __forceinline__ void mbar_wait_long(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (++spins > (1u << 26)) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ===================================================================== epilogue (warps 2..5), once
     const int q = warp & 3;
     const int ci = 128 * mb + q * 32 + lane;
-    mbar_wait(bar_done, 0);
+    mbar_wait_long(bar_done, 0);
     tc_fence_after();
     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int t = 0; t < ntap; ++t) {
