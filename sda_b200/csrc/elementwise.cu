@@ -77,28 +77,40 @@ __global__ void unpack_nchw_kernel(const float* __restrict__ f, float* __restric
 }
 
 // F(C) -> OP(C).  kind 0: normal; 1: S2 parity layout; 2: zero-insertion x2 (f is at H/2 x W/2).
+// One thread converts 8 consecutive channels of one pixel: two 16 B loads, one 16 B store per plane
+// (and per halo replica) -- the 32 channels of a K-block are 64 contiguous bytes in either layout.
 __global__ void f_to_operand_kernel(const float* __restrict__ f, bf16* __restrict__ op, int N, int H, int W, int C,
                                     int kind) {
-  const size_t warp = (size_t)blockIdx.x * kWarpsPerBlock + threadIdx.y;
-  const size_t total = (size_t)N * H * W;
-  if (warp >= total) return;
-  const int lane = threadIdx.x;
-  const int w = warp % W, h = (warp / W) % H, n = warp / ((size_t)W * H);
+  const int groups = C >> 3;
+  const size_t total = (size_t)N * H * W * groups;
   const OpShape s{N, H, W, C, kind == 1};
-  const float* src = nullptr;
-  if (kind == 2) {
-    if (!(h & 1) && !(w & 1)) src = f + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C;
-  } else {
-    src = f + warp * C;
-  }
-  for (int c = lane; c < C; c += 32) {
-    bf16 hi, lo;
-    split_bf16(src ? src[c] : 0.f, hi, lo);
-    const size_t blk = (size_t)(c >> 5) * s.block_stride() + lane;
+  const size_t lo_off = s.lo_offset();
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int g = (int)(t % groups);
+    const size_t pix = t / groups;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((size_t)W * H));
+    const int c = g << 3;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* src = nullptr;
+    if (kind == 2) {
+      if (!(h & 1) && !(w & 1)) src = f + (((size_t)n * (H / 2) + h / 2) * (W / 2) + w / 2) * C + c;
+    } else {
+      src = f + pix * C + c;
+    }
+    if (src) {
+      const float4 a = reinterpret_cast<const float4*>(src)[0], b = reinterpret_cast<const float4*>(src)[1];
+      v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+    }
+    uint4 hi, lo;
+    split_bf16x2(v[0], v[1], hi.x, lo.x);
+    split_bf16x2(v[2], v[3], hi.y, lo.y);
+    split_bf16x2(v[4], v[5], hi.z, lo.z);
+    split_bf16x2(v[6], v[7], hi.w, lo.w);
+    const size_t blk = (size_t)(c >> 5) * s.block_stride() + (c & 31);
     for_each_replica(h, w, H, W, [&](int hp, int wp) {
       bf16* dst = op + op_offset(s, n, hp, wp) + blk;
-      dst[0] = hi;
-      dst[s.lo_offset()] = lo;
+      *reinterpret_cast<uint4*>(dst) = hi;
+      *reinterpret_cast<uint4*>(dst + lo_off) = lo;
     });
   }
 }
@@ -398,7 +410,9 @@ int unpack_f_to_nchw(const float* f, float* x, int N, int Creal, int Cpad, int H
 }
 
 int f_to_operand(const float* f, bf16* op, int N, int H, int W, int C, int kind, cudaStream_t st) {
-  f_to_operand_kernel<<<warp_grid((size_t)N * H * W), dim3(32, kWarpsPerBlock), 0, st>>>(f, op, N, H, W, C, kind);
+  const size_t threads = (size_t)N * H * W * (C / 8);
+  const size_t blocks = (threads + 255) / 256;
+  f_to_operand_kernel<<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, st>>>(f, op, N, H, W, C, kind);
   SDAB_LAUNCH_CHECK("f_to_operand_kernel");
   return SDAB_OK;
 }
