@@ -342,7 +342,10 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
 
   // one modulated residual block: cur -> dst (F); dst_op: also the raw operand of dst; next_j: the
   // block that consumes dst (its LayerNorm is fused into conv2), or -1
-  auto block = [&](int d, int j, int c1, const float* cur, float* dst, bf16* dst_op, int next_j) -> int {
+  // tail_ln: dst feeds the tail of level d > 0 (LN -> nearest x2 -> conv, sda/nn.py:161-170): its shift-free
+  // LayerNorm is fused into conv2 as well and lands in upop[d]
+  auto block = [&](int d, int j, int c1, const float* cur, float* dst, bf16* dst_op, int next_j,
+                   bool tail_ln = false) -> int {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
     bf16* aop = save ? OP(p.aop[j]) : OP(p.aop_tmp[d]);
     if (prenorm != j)
@@ -358,6 +361,11 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
     r.mode = mode;
     r.epi.bias = bias(c1 + 1), r.epi.res = cur, r.epi.outF = dst, r.epi.outOP = dst_op;
     if (!dst_op) fuse_ln(r, next_j);
+    if (tail_ln) {
+      r.epi.ln = 1, r.epi.ln_shift = nullptr, r.epi.ln_shift_stride = 0, r.epi.ln_nt = 1;
+      r.epi.ln_rstd_out = save ? F(p.rstd_tail[d]) : nullptr;
+      r.epi.outOP = OP(p.upop[d]);
+    }
     return run_conv(engine, r, st);
   };
 
@@ -392,7 +400,8 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       float* dst = cur == F(p.x0[d]) ? F(p.x1[d]) : F(p.x0[d]);
       const bool fin = d == 0 && b == nb - 1;
       const int next_j = b + 1 < nb ? h->asc_blk[d][b + 1] : -1;
-      SDAB_TRY(block(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst, fin ? OP(p.finop) : nullptr, next_j));
+      SDAB_TRY(block(d, h->asc_blk[d][b], h->asc_c1[d][b], cur, dst, fin ? OP(p.finop) : nullptr, next_j,
+                     fuse && d > 0 && b == nb - 1));
       have_finop = have_finop || fin;
       cur = dst;
     }
@@ -401,7 +410,8 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       // tail = LN -> nearest x2 -> conv (sda/nn.py:161-170) in sub-pixel form: the LayerNorm output stays
       // at the LOW resolution and each output parity (po, pp) is a 2x2-tap conv with summed weights
       // (4 / 9 of the FLOPs, a quarter of the operand traffic)
-      SDAB_TRY(ln_forward(cur, nullptr, 0, 1, OP(p.upop[d]), save ? F(p.rstd_tail[d]) : nullptr, N, Hd, Wd, C, 0, st));
+      if (nb == 0)  // otherwise produced by the epilogue of the level's last block (tail_ln)
+        SDAB_TRY(ln_forward(cur, nullptr, 0, 1, OP(p.upop[d]), save ? F(p.rstd_tail[d]) : nullptr, N, Hd, Wd, C, 0, st));
       const int next_j = h->d.hidden_blocks[d - 1] > 0 ? h->asc_blk[d - 1][0] : -1;
       for (int cls = 0; cls < 4; ++cls) {
         const int po = cls >> 1, pp = cls & 1;
