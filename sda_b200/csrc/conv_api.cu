@@ -17,7 +17,7 @@ struct ConvWs {
 ConvWs conv_ws(int N, int Cin, int Cout, int H, int W, int stride, int transpose) {
   // transpose: the "convolution" maps Cout -> Cin channels with the flipped kernel (stride 1 only)
   const int ci = transpose ? Cout : Cin, co = transpose ? Cin : Cout;
-  const int K = round_up(ci, 32), Nn = round_up(co, 16);
+  const int K = round_up(ci, 32), Nn = round_up(co, 32);
   ConvWs w;
   size_t off = 0;
   auto take = [&](size_t b) {
@@ -26,8 +26,8 @@ ConvWs conv_ws(int N, int Cin, int Cout, int H, int W, int stride, int transpose
     return o;
   };
   w.in_op = take(OpShape{N, H, W, K, 0}.bytes());
-  w.wf = take((size_t)9 * round_up(Cin, 32) * round_up(Cout, 16) * 2 * sizeof(bf16));
-  w.wb = take((size_t)9 * round_up(Cout, 32) * round_up(Cin, 16) * 2 * sizeof(bf16));
+  w.wf = take((size_t)9 * round_up(Cin, 32) * round_up(Cout, 32) * 2 * sizeof(bf16));
+  w.wb = take((size_t)9 * round_up(Cout, 32) * round_up(Cin, 32) * 2 * sizeof(bf16));
   w.bias = take((size_t)Nn * sizeof(float));
   w.outf = take((size_t)N * (H / stride) * (W / stride) * Nn * sizeof(float));
   w.total = off;
@@ -57,7 +57,7 @@ int sdab_conv3x3(const float* x, const float* weight, const float* bias, float* 
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)workspace;
   const int ci = transpose ? Cout : Cin, co = transpose ? Cin : Cout;
-  const int K = round_up(ci, 32), Nn = round_up(co, 16);
+  const int K = round_up(ci, 32), Nn = round_up(co, 32);
   SDAB_TRY(pack_nchw_to_op(x, (bf16*)(ws + w.in_op), N, ci, K, H, W, stride == 2, st));
   SDAB_TRY(pack_conv_weights(weight, (bf16*)(ws + w.wf), (bf16*)(ws + w.wb), Cout, Cin, st));
   SDAB_TRY(fill_zero(ws + w.bias, (size_t)Nn * sizeof(float), st));

@@ -310,12 +310,13 @@ __global__ void time_shifts_kernel(const float* __restrict__ y, const float* __r
 //   bwd[tap][chunk][plane][ci][kc]  = split(W[32 chunk + kc][ci][2-a][2-b])   (transposed, flipped:
 //        the input-gradient of a circular stride-1 correlation is the correlation of the cotangent
 //        with this kernel)
-// Rows/K are zero padded to multiples of 16 / 32.
+// Rows and K are zero padded to multiples of 32 (so that every convolution, including the 10-channel
+// final one and the 11-channel head transpose, qualifies for the CTA-pair patch kernel).
 // ---------------------------------------------------------------------------------------------
 __global__ void pack_conv_weights_kernel(const float* __restrict__ w, bf16* __restrict__ fwd, bf16* __restrict__ bwd,
                                          int Cout, int Cin) {
-  const int Kf = (Cin + 31) / 32 * 32, Nf = (Cout + 15) / 16 * 16;
-  const int Kb = (Cout + 31) / 32 * 32, Nb = (Cin + 15) / 16 * 16;
+  const int Kf = (Cin + 31) / 32 * 32, Nf = (Cout + 31) / 32 * 32;
+  const int Kb = (Cout + 31) / 32 * 32, Nb = (Cin + 31) / 32 * 32;
   const size_t nf = (size_t)9 * Kf * Nf, nb = (size_t)9 * Kb * Nb;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nb; i += (size_t)gridDim.x * blockDim.x) {
     const bool is_b = i >= nf;

@@ -21,8 +21,8 @@ namespace sdab {
 
 struct ConvLayer {
   int cin, cout;        // real channels
-  int kf, nf;           // forward GEMM K (ceil32 cin), N (ceil16 cout)
-  int kb, nb;           // backward GEMM K (ceil32 cout), N (ceil16 cin)
+  int kf, nf;           // forward GEMM K (ceil32 cin), N (ceil32 cout)
+  int kb, nb;           // backward GEMM K (ceil32 cout), N (ceil32 cin)
   size_t off_fwd, off_bwd, off_bias;  // byte offsets in the packed buffer
   size_t off_tf = 0, off_tb = 0;      // tails (d > 0): combined sub-pixel / transposed 4x4 weights (16 taps each)
   bool is_tail = false;
@@ -86,7 +86,7 @@ Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save, bool 
   const int D = h->d.depth;
   p.D = D;
   Arena a;
-  const int kin0 = round_up(h->d.in_channels, 32), nout = round_up(h->d.out_channels, 16);
+  const int kin0 = round_up(h->d.in_channels, 32), nout = round_up(h->d.out_channels, 32);
   p.in_op = a.take(op_bytes(N, H, W, kin0));
   p.shift = a.take((size_t)Nt * h->shift_rows * sizeof(float));
   p.finop = a.take(op_bytes(N, H, W, h->d.hidden_channels[0]));
@@ -124,7 +124,7 @@ Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save, bool 
     per_level(h->desc_blk);
     per_level(h->asc_blk);
     p.gout_op = a.take(op_bytes(N, H, W, round_up(h->d.out_channels, 32)));
-    p.gxf = a.take(f_bytes(N, H, W, round_up(h->d.in_channels, 16)));
+    p.gxf = a.take(f_bytes(N, H, W, round_up(h->d.in_channels, 32)));
     for (int d = 0; d < D; ++d) {
       const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
       p.gc1op[d] = a.take(op_bytes(N, Hd, Wd, C));
@@ -189,8 +189,8 @@ int sdab_unet_create(const sdab_unet_desc* desc, sdab_unet** out) {
   auto add_conv = [&](int cin, int cout) {
     ConvLayer c{};
     c.cin = cin, c.cout = cout;
-    c.kf = round_up(cin, 32), c.nf = round_up(cout, 16);
-    c.kb = round_up(cout, 32), c.nb = round_up(cin, 16);
+    c.kf = round_up(cin, 32), c.nf = round_up(cout, 32);
+    c.kb = round_up(cout, 32), c.nb = round_up(cin, 32);
     h->convs.push_back(c);
     return (int)h->convs.size() - 1;
   };
