@@ -127,9 +127,13 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------ CPU baseline
-def cpu_step_seconds(n_steps: int, warm: int):
+CPU_WINDOWS = 2  # windows of the bounded CPU sample (L = 6); BASELINE.md section 5 plans a 2-window slice
+
+
+def cpu_step_seconds(n_steps: int, warm: int, windows: int = CPU_WINDOWS):
     r"""Seconds per denoising step of the oracle (reference algorithm, torch CPU, all host threads) on a
-    ONE-window slice (L = 5) of the 256 x 256 workload.  Returns (seconds per sample step, cores)."""
+    `windows`-window slice (L = windows + 4) of the 256 x 256 workload.  Returns (seconds per sample
+    step, cores)."""
 
     from oracle import score_oracle as so
 
@@ -138,7 +142,7 @@ def cpu_step_seconds(n_steps: int, warm: int):
     score = make_score(SIZE, 'cpu')
     state = {k[len('kernel.'):]: v for k, v in score.state_dict().items()}
     k = WINDOW // 2
-    x, y = synthetic(1, WINDOW, SIZE)
+    x, y = synthetic(1, windows + 2 * k, SIZE)
     eps_fn = lambda a, b: so.gaussian_score(lambda c, d: so.mc_score(state, c, d, k), y, observation, 0.1, a, b, gamma=1e-2)  # noqa: E731
     g = torch.Generator().manual_seed(1)
     noise = [torch.randn(x.shape, generator=g) for _ in range((n_steps + warm) * CORRECTIONS)]
@@ -156,15 +160,153 @@ def cpu_step_seconds(n_steps: int, warm: int):
     return sum(timed) / len(timed), cores
 
 
+def gpu_eager_baseline(device) -> dict:
+    r"""The "kernel to beat" on the same box: the reference
+    algorithm as stock PyTorch-eager CUDA ops (the oracle port moved to the GPU: F.pad(circular) + cuDNN conv2d,
+    ATen LayerNorm chain, autograd for the input-gradient), same network, inputs and guided step, with cuDNN /
+    cuBLAS TF32 allowed (PyTorch's default for convolutions) and disallowed.  The autograd state of 60 windows
+    at 256 x 256 does not fit 180 GB, and windows are independent, so the step is timed on a slice of `nw`
+    windows and scaled linearly.  Also reports each mode's guided-score rel-L2 against the fp32 CPU oracle on a
+    2-window slice: the parity bar the repo's own path is held to is 1e-4."""
+
+    from oracle import score_oracle as so
+    from oracle.testing import rel_l2
+
+    k = WINDOW // 2
+    windows = LENGTH - 2 * k
+    score = make_score(SIZE, 'cpu')
+    state_cpu = {n[len('kernel.'):]: v for n, v in score.state_dict().items()}
+    state = {n: v.to(device) for n, v in state_cpu.items()}
+    flags = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    out = {'kind': 'reference algorithm (oracle port), PyTorch eager on the same GPU', 'unit': 'steps/s'}
+
+    # parity sample: L = 6 (2 windows) guided score, CPU fp32 oracle as the yardstick
+    xs, ys = synthetic(1, 2 + 2 * k, SIZE)
+    ts = torch.tensor(0.5)
+    ref = so.gaussian_score(lambda a, b: so.mc_score(state_cpu, a, b, k), ys, observation, 0.1, xs, ts, gamma=1e-2)
+
+    try:
+        for tf32 in (True, False):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            name = 'tf32' if tf32 else 'fp32'
+            got = so.gaussian_score(lambda a, b: so.mc_score(state, a, b, k), ys.to(device), observation, 0.1,
+                                    xs.to(device), ts.to(device), gamma=1e-2)
+            out[f'{name}_rel_l2_vs_cpu_fp32'] = rel_l2(got, ref)
+            del got
+
+            for nw in (12, 6, 3):
+                try:
+                    x, y = synthetic(1, nw + 2 * k, SIZE)
+                    x, y = x.to(device), y.to(device)
+                    eps_fn = lambda a, b: so.gaussian_score(lambda c, d: so.mc_score(state, c, d, k), y, observation, 0.1, a, b, gamma=1e-2)  # noqa: E731
+                    g = torch.Generator().manual_seed(1)
+                    noise = [torch.randn(x.shape, generator=g).to(device) for _ in range(3)]
+                    so.pc_sample(eps_fn, x, steps=SCHEDULE_STEPS, corrections=CORRECTIONS, tau=TAU, noise=noise[:1], n_steps=1)
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for i in range(2):
+                        so.pc_sample(eps_fn, x, steps=SCHEDULE_STEPS, corrections=CORRECTIONS, tau=TAU, noise=noise[1 + i:2 + i], n_steps=1)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    sec = e0.elapsed_time(e1) * 1e-3 / 2
+                    out[name] = 1.0 / (sec * windows / nw)
+                    out[f'{name}_sample'] = f'2 denoising steps on a {nw}-window slice (L={nw + 4}), {sec * 1e3:.0f} ms each, scaled x{windows / nw:g}'
+                    break
+                except torch.cuda.OutOfMemoryError:
+                    torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flags
+
+    out['flags'] = {'cudnn.allow_tf32 / cuda.matmul.allow_tf32': 'True for the tf32 entry, False for the fp32 entry',
+                    'cudnn.benchmark': torch.backends.cudnn.benchmark, 'torch': torch.__version__,
+                    'cudnn': torch.backends.cudnn.version()}
+    torch.cuda.empty_cache()
+
+    return out
+
+
+def secondary(device) -> dict:
+    r"""The two other measured paths, timed by the same run so that the driver sees them (not the headline):
+    the Kolmogorov stepper (BASELINE config 4 per-GPU share: 128 members, 256 x 256, dt = 0.2) against the HBM
+    roofline of its streaming formulation (16 N^2 bytes per member and inner step), and
+    one training iteration (BASELINE config 5 per-GPU share: batch 32 at 64 x 64, VPSDE.loss + backward +
+    AdamW) against the tensor roofline (3 x forward FLOPs)."""
+
+    import sda_b200.score as sc
+    from sda_b200.mcs import KolmogorovFlow
+
+    peaks_file = ROOT / 'MEASURED_PEAKS.json'
+    peaks = json.loads(peaks_file.read_text()) if peaks_file.exists() else {}
+    hbm, tflops = float(peaks.get('hbm_gbs', 6550.0)), float(peaks.get('bf16_tflops_sustained', 1400.0))
+    out = {}
+
+    size, E, transitions = 256, 128, 4
+    chain = KolmogorovFlow(size=size, dt=0.2)
+    x = chain.prior((E,)).to(device)
+    chain.trajectory(x, 1, last=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    y = chain.trajectory(x, transitions, last=True)
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3
+    rate = transitions * chain.steps * E / sec
+    gbs = rate * 16 * size * size / 1e9
+    out['stepper'] = {
+        'workload': f'KolmogorovFlow(size={size}, dt=0.2), {E} members, {transitions} transitions x {chain.steps} inner steps',
+        'member_inner_steps_per_s': rate, 'member_transitions_per_s': transitions * E / sec, 'finite': bool(torch.isfinite(y).all()),
+        'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': gbs / hbm, 'traffic': None,
+                     'note': 'algorithmic bytes = 16 N^2 per member and inner step (read + write u, v once)'},
+    }
+    del x, y, chain
+    torch.cuda.empty_cache()
+
+    score = make_score(64, device)
+    sde = sc.VPSDE(score.kernel, shape=(10, 64, 64)).to(device).train()
+    opt = torch.optim.AdamW(sde.parameters(), lr=2e-4, weight_decay=1e-3, fused=True)
+    xb = torch.randn(32, 10, 64, 64, device=device, generator=torch.Generator(device=device).manual_seed(0))
+
+    def it():
+        l = sde.loss(xb)
+        opt.zero_grad(set_to_none=True)
+        l.backward()
+        opt.step()
+
+    for _ in range(3):
+        it()
+
+    torch.cuda.synchronize()
+    iters = 8
+    e0.record()
+    for _ in range(iters):
+        it()
+    e1.record()
+    torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / iters
+    tf = 3 * 32 * CONV_FLOP_PER_PIXEL * 64 * 64 / sec / 1e12
+    out['training'] = {
+        'workload': 'VPSDE.loss + backward + AdamW, windows (10, 64, 64), batch 32, mode ' + os.environ.get('SDAB_MODE', 'bf16x3'),
+        'ms_per_iteration': sec * 1e3, 'samples_per_s': 32 / sec,
+        'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': tflops, 'unit': 'TFLOP/s', 'frac': tf / tflops, 'traffic': None,
+                     'note': 'algorithmic FLOPs = 3 x forward convolution FLOPs (forward, input-gradient, weight-gradient)'},
+    }
+
+    return out
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
 
     windows = LENGTH - 2 * (WINDOW // 2)
-    sec, cores = cpu_step_seconds(args.steps, args.warmup)
-    value = 1.0 / (sec * windows)
-    sample = (f'one denoising step (2 guided score evaluations, U-Net forward + input-gradient) on a 1-window slice '
-              f'(L={WINDOW}) of the {SIZE}x{SIZE} workload, scaled x{windows} windows')
+    nw = windows if args.full_cpu else CPU_WINDOWS
+    sec, cores = cpu_step_seconds(args.steps, args.warmup, nw)
+    value = 1.0 / (sec * windows / nw)
+    sample = (f'one denoising step (2 guided score evaluations, U-Net forward + input-gradient) on a {nw}-window slice '
+              f'(L={nw + 4}) of the {SIZE}x{SIZE} workload, {sec:.2f} s per sample step, scaled x{windows / nw:g}')
     print(json.dumps({
         'impl': 'reference',
         'metric': 'denoising steps/sec, Kolmogorov 256x256 L=64 guided posterior sampling',
@@ -269,6 +411,11 @@ def run_ours(args, rank, local_rank, world):
     lib.sdab_conv_profile(0)
     clocks = sampler.stop() if rank == 0 else None
     assert os.environ.get('SDAB_UMMA_DEBUG') or torch.isfinite(x).all(), 'non-finite state after the timed steps'
+    # proof carried by the line itself: the state after warmup + steps denoising steps.  The sharded path is
+    # bit-identical to the single-GPU one, so this hash is the same at N = 1, 2, 4, 8 for equal --steps / --warmup
+    import hashlib
+
+    state_sha = hashlib.sha256(x.cpu().numpy().tobytes()).hexdigest()[:16]
 
     # ---------------- end to end through the public step API, host buffers in and out
     barrier()
@@ -317,7 +464,7 @@ def run_ours(args, rank, local_rank, world):
         'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
         'e2e': {'value': args.steps / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': x_pin.numel() * 4 + y_pin.numel() * 4,
                 'd2h_bytes_per_step': x_pin.numel() * 4},
-        'gpu_launches': int(launches),
+        'gpu_launches': int(launches), 'state_sha': state_sha,
         'roofline': {
             'bound': 'tensor', 'kernel': 'conv_umma_patch_kernel (+ conv_umma_kernel for strided / sub-pixel layers)', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
@@ -329,13 +476,17 @@ def run_ours(args, rank, local_rank, world):
     }
 
     if world == 1 and not args.no_cpu_baseline and args.variant == 'guided':
-        sec, cores = cpu_step_seconds(2, 0)
+        sec, cores = cpu_step_seconds(2, 1)
         windows = LENGTH - 2 * (WINDOW // 2)
         out['cpu_baseline'] = {
-            'value': 1.0 / (sec * windows * args.batch), 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
-            'sample': f'2 denoising steps of the torch-CPU oracle on a 1-window slice (L={WINDOW}) at {SIZE}x{SIZE}, '
-                      f'{sec:.1f} s each, scaled x{windows * args.batch} windows',
+            'value': 1.0 / (sec * windows * args.batch / CPU_WINDOWS), 'unit': 'steps/s', 'cores': cores, 'kind': 'port',
+            'sample': f'2 denoising steps (after 1 warm-up) of the torch-CPU oracle on a {CPU_WINDOWS}-window slice '
+                      f'(L={CPU_WINDOWS + 4}) at {SIZE}x{SIZE}, {sec:.1f} s each, scaled x{windows * args.batch / CPU_WINDOWS:g}',
         }
+        out['gpu_eager_baseline'] = gpu_eager_baseline(device)
+
+    if world == 1 and not args.no_secondary and args.variant == 'guided':
+        out['secondary'] = secondary(device)
 
     print(json.dumps(out))
 
@@ -350,7 +501,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1, help='trajectories sampled together (B)')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline and gpu_eager_baseline legs')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the stepper / training measurements')
+    ap.add_argument('--full-cpu', action='store_true', help='--impl reference: time all 60 windows (about 90 s per step)')
     ap.add_argument('--variant', default='guided', choices=sorted(VARIANTS),
                     help='guided is the BASELINE metric; the others are reported beside it (SURVEY.md section 8d)')
     args = ap.parse_args()

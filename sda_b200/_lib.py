@@ -96,13 +96,14 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     if _lib is not None:
         return _lib
 
-    if not LIB_PATH.exists():
-        if not build_if_missing or os.environ.get('SDAB_NO_BUILD'):
-            raise RuntimeError(f'{LIB_PATH} is missing: run `python -m sda_b200.build` (there is no CPU fallback)')
-
+    # build() returns at once when the source digest matches its stamp, and rebuilds a stale library
+    # after an edit of csrc/ or a pull (a stale .so with changed signatures would otherwise be loaded)
+    if build_if_missing and not os.environ.get('SDAB_NO_BUILD'):
         from . import build as _build
 
         _build.build()
+    elif not LIB_PATH.exists():
+        raise RuntimeError(f'{LIB_PATH} is missing: run `python -m sda_b200.build` (there is no CPU fallback)')
 
     lib = ctypes.CDLL(str(LIB_PATH))
 

@@ -56,6 +56,25 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
 
+    # one builder at a time (the ranks of a torchrun job all call load()); the others wait, then
+    # find the stamp up to date
+    import fcntl
+
+    lock = open(OBJ / 'lock', 'w')
+    fcntl.flock(lock, fcntl.LOCK_EX)
+
+    try:
+        if not force and LIB.exists() and stamp.exists() and stamp.read_text() == digest:
+            return LIB
+
+        return _build_locked(nvcc, stamp, digest, verbose)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(nvcc: str, stamp: Path, digest: str, verbose: bool) -> Path:
+
     def compile_one(src: str) -> Path:
         obj = OBJ / (src + '.o')
         cmd = [nvcc, *NVCC_FLAGS, '-c', str(CSRC / src), '-o', str(obj)]

@@ -161,8 +161,10 @@ class _UNetFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x: Tensor, y: Tensor, net: 'UNet', *params: Tensor) -> Tensor:
-        train = any(ctx.needs_input_grad[1:]) and not getattr(_scope, 'input_only', False)
-        save = 2 if train else int(bool(ctx.needs_input_grad[0]))
+        # grad mode is always off inside Function.forward: UNet.forward recorded the caller's
+        grad = getattr(_scope, 'grad_enabled', True)
+        train = grad and any(ctx.needs_input_grad[1:]) and not getattr(_scope, 'input_only', False)
+        save = 2 if train else int(grad and bool(ctx.needs_input_grad[0]))
         out = net._native_forward(x, y, save)
         ctx.net = net
         ctx.save = save
@@ -356,6 +358,24 @@ class UNet(nn.Module):
 
         return state
 
+    def invalidate_packed(self) -> None:
+        r"""Forces the bf16-packed weight copies to be rebuilt at the next forward.  The cache is keyed on
+        (data_ptr, version) of every parameter, which in-place updates through `.data` (EMA, weight
+        surgery) do not change: call this after such an update.  `load_state_dict`, `.to()`, `.cuda()`
+        and friends call it themselves.  SDAB_ALWAYS_REPACK=1 repacks at every forward."""
+
+        self._packed_key = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed_key = None
+
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._packed_key = None
+
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _ensure_handle(self, device: torch.device):
         lib = _lib.load()
 
@@ -378,7 +398,7 @@ class UNet(nn.Module):
         params = [p for m in convs + projs for p in (m.weight, m.bias)]
         key = (device, tuple((p.data_ptr(), p._version) for p in params))
 
-        if key != self._packed_key:
+        if key != self._packed_key or os.environ.get('SDAB_ALWAYS_REPACK'):
             for p in params:
                 if p.device != device or p.dtype != torch.float32:
                     raise RuntimeError('sda_b200.nn.UNet: parameters must be float32 on the same CUDA device as the input')
@@ -514,8 +534,15 @@ class UNet(nn.Module):
 
         convs, projs = self._ordered_parameters()
         params = [p for m in convs + projs for p in (m.weight, m.bias)]
+        # under torch.no_grad() (unguided sampling, GaussianScore(detach=True), validation) nothing can
+        # ever back-propagate: the forward must not save activations although needs_input_grad is set
+        prev = getattr(_scope, 'grad_enabled', True)
+        _scope.grad_enabled = torch.is_grad_enabled()
 
-        return _UNetFunction.apply(x, y, self, *params)
+        try:
+            return _UNetFunction.apply(x, y, self, *params)
+        finally:
+            _scope.grad_enabled = prev
 
     def __del__(self):
         handle = getattr(self, '_handle', None)

@@ -296,6 +296,9 @@ class VPSDE(nn.Module):
         # initial noise drawn on the CPU then moved, as the reference does (score.py:243)
         x = torch.randn(shape + tuple(self.shape)).to(self.device)
         x = x.reshape(-1, *self.shape).contiguous()
+        # window-sharded evaluation (sda_b200.parallel) needs a bit-identical state on every rank:
+        # rank 0's draw wins, whatever the ranks' own generators hold
+        x = self._from_shard_root(x)
 
         state = self.sampler_state(x, steps)
         iterator = range(steps)
@@ -333,9 +336,29 @@ class VPSDE(nn.Module):
             state['scratch'] = torch.empty(
                 lib.sdab_vpsde_correct_scratch_floats(x.shape[0]), dtype=torch.float32, device=x.device
             )
-            state['seed'] = int(torch.randint(0, 2**62, (), dtype=torch.int64))  # torch's CPU generator
+            seed = torch.randint(0, 2**62, (1,), dtype=torch.int64)  # torch's CPU generator
+            state['seed'] = int(self._from_shard_root(seed.to(x.device)))
 
         return state
+
+    def _from_shard_root(self, v: Tensor) -> Tensor:
+        r"""Broadcasts `v` from the first rank of the shard group when `eps` contains a window-sharded
+        MCScoreNet (identity otherwise): the ranks of a sharded sampler must agree on the initial noise
+        and on the Philox seed, and torchrun does not seed them identically."""
+
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return v
+
+        for m in self.eps.modules():
+            if getattr(m, '_sdab_sharded', False) and dist.get_world_size(m.shard_group) > 1:
+                src = 0 if m.shard_group is None else dist.get_global_rank(m.shard_group, 0)
+                v = v.contiguous()
+                dist.broadcast(v, src=src, group=m.shard_group)
+                break
+
+        return v
 
     def denoise_step(self, x: Tensor, i: int, state: dict, c: Tensor = None, corrections: int = 0, tau: float = 1.0) -> Tensor:
         r"""One iteration of the sampling loop (score.py:250-261): predictor + `corrections` Langevin
