@@ -339,7 +339,10 @@ def test_detached_guidance_matches_oracle():
     A = lambda v: v[..., ::2, ::2]  # noqa: E731
     ref = so.gaussian_score(lambda a, b: so.mc_score(state, a, b, k), y, A, 0.1, x, t, gamma=1e-2, detach=True)
     guided = sc.GaussianScore(y.cuda(), A=A, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2, detach=True).cuda()
-    out = guided(x.cuda(), t.cuda())
+
+    with torch.no_grad():  # as VPSDE.sample calls it (sda/score.py:249)
+        out = guided(x.cuda(), t.cuda())
+
     assert rel_l2(out, ref) < TOL
     # nothing was saved for a backward that can never come
     assert score.kernel.network._saved_level == 0
