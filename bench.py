@@ -421,7 +421,7 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     t0 = time.perf_counter()
 
-    for _ in range(args.steps):
+    for _ in range(0 if args.profile_run else args.steps):
         x.copy_(x_pin, non_blocking=True)
         if guided is not None:
             guided.y.copy_(y_pin, non_blocking=True)
@@ -462,7 +462,7 @@ def run_ours(args, rank, local_rank, world):
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'bf16x3 (split-bf16 operands, fp32 accumulate)' if passes == 3 else 'bf16 (fp32 accumulate)',
         'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
-        'e2e': {'value': args.steps / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': x_pin.numel() * 4 + y_pin.numel() * 4,
+        'e2e': {'value': None if args.profile_run else args.steps / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': x_pin.numel() * 4 + y_pin.numel() * 4,
                 'd2h_bytes_per_step': x_pin.numel() * 4},
         'gpu_launches': int(launches), 'state_sha': state_sha,
         'roofline': {
@@ -474,6 +474,10 @@ def run_ours(args, rank, local_rank, world):
             'conv_share_of_step': conv_ms.value / ms,
         },
     }
+
+    if args.profile_run:
+        args.no_cpu_baseline = args.no_secondary = True
+        out['profile_run'] = 'under a profiler: not a bench value'
 
     if world == 1 and not args.no_cpu_baseline and args.variant == 'guided':
         sec, cores = cpu_step_seconds(2, 1)
@@ -503,6 +507,7 @@ def main():
     ap.add_argument('--batch', type=int, default=1, help='trajectories sampled together (B)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline and gpu_eager_baseline legs')
     ap.add_argument('--no-secondary', action='store_true', help='skip the stepper / training measurements')
+    ap.add_argument('--profile-run', action='store_true', help='for runs under ncu: one warm-up step allowed, no e2e / baseline legs (not a bench value)')
     ap.add_argument('--full-cpu', action='store_true', help='--impl reference: time all 60 windows (about 90 s per step)')
     ap.add_argument('--variant', default='guided', choices=sorted(VARIANTS),
                     help='guided is the BASELINE metric; the others are reported beside it (SURVEY.md section 8d)')
@@ -511,7 +516,7 @@ def main():
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
-    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    args.warmup = max(args.warmup, 1 if args.profile_run else 3) if args.impl == 'ours' else args.warmup
 
     if args.impl == 'reference':
         run_reference(args, rank)

@@ -69,6 +69,7 @@ struct UmmaParams {
   int a_stages;    // patch kernel: depth of the patch ring (`stages` is the depth of the weight ring)
   uint32_t b_stage_bytes;
   int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
+  uint32_t ctrl_bytes;  // control block in front of the staging tiles (barriers, TMEM slot, csplit statistics exchange)
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
@@ -213,6 +214,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 }
 
+// 32 consecutive fp32 columns of this thread's TMEM lane written back (the LayerNorm epilogues park values
+// next to / in place of the accumulator between their two passes); tmem_st_wait before reading them again
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+      "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])),
+      "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])),
+      "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+      "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
+      "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
+      "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
                "r"(c0), "r"(c1), "r"(c2)
@@ -289,13 +310,6 @@ __device__ __forceinline__ void load32(const float* __restrict__ src, float (&o)
     o[4 * j] = t.x, o[4 * j + 1] = t.y, o[4 * j + 2] = t.z, o[4 * j + 3] = t.w;
   }
 }
-__device__ __forceinline__ void load32_ldg(const float* __restrict__ src, float (&o)[32]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(src + 4 * j));
-    o[4 * j] = t.x, o[4 * j + 1] = t.y, o[4 * j + 2] = t.z, o[4 * j + 3] = t.w;
-  }
-}
 __device__ __forceinline__ void load32_hilo(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float (&o)[32]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -313,9 +327,9 @@ __device__ __forceinline__ void load32_hilo(const bf16* __restrict__ hi, const b
 
 
 // ------------------------------------------------------------------------------------------ epilogue
-// Epilogue role (warps 2..5 of both kernels): TMEM -> registers -> fused bias / residual / activation /
-// activation-derivative / LayerNorm (forward or adjoint) / bf16 split -> staged TMA stores.
-template <int LN, bool CTA2>
+// Epilogue role (warps 2..5 of both kernels) of the convolutions without a fused LayerNorm: TMEM -> registers ->
+// fused bias / residual / activation / activation-derivative / bf16 split -> staged TMA stores.
+template <bool CTA2>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
                                               uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
                                               uint32_t acc_stride, uint32_t staging_base, int tile_begin, int tile_end,
@@ -361,8 +375,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
       const bool wantO = p.epi.outOP != nullptr;
       const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
       const OpShape so{0, p.Ho, p.Wo, p.Cout, 0};
-      constexpr int ln = LN;  // fused LayerNorm variant (ConvEpilogue::ln), compile-time to keep registers down
-      // developer ablation bits: 8 = no LayerNorm statistics pass, 16 = no global operand loads, 32 = no stores
+      // developer ablation bits: 16 = no global operand loads, 32 = no stores
       const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
       {
         // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
@@ -376,74 +389,14 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
             const float* pf = p.epi.res ? p.epi.res : p.epi.dact;
             if (pf)
               for (int c = 0; c < p.Cout; c += 32) prefetch_l2(pf + npix * p.Cout + c);
-            if (ln == 2) {
-              const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
-              for (int c = 0; c < 2 * p.out_chunks; ++c) prefetch_l2(pa + (size_t)c * so.block_stride());
-            }
           }
         }
-      }
-      const float invC = 1.f / (float)p.Cout, invC1 = 1.f / (float)(p.Cout - 1);
-      // fused LayerNorm statistics (first pass over the accumulator)
-      float st_a = 0.f, st_b = 0.f, st_r = 1.f;  // forward: mean, -, rstd ; backward: mean(g), sum(g a)/(C-1), rstd
-      const float* shiftp =
-          (ln == 1 && p.epi.ln_shift) ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride
-                                      : nullptr;
-      const bf16* a_pix = (ln == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
-      if (ln == 1 && !(p.debug & 8)) {
-        float s1 = 0.f, s2 = 0.f, K = 0.f;
-        for (int cc = 0; cc < p.out_chunks; ++cc) {
-          float v[32], f[32], rr[32];
-          if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
-          tmem_ld32(t0 + cc * 32, v);
-          epilogue_math32(p.epi, v, f, rr, has_res, false, cc * 32);
-          if (shiftp) {
-            float sh[32];
-            load32_ldg(shiftp + cc * 32, sh);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += sh[j];
-          }
-          if (cc == 0) K = f[0];  // shifted one-pass variance: accumulate around the first channel
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float u = f[j] - K;
-            s1 += u;
-            s2 += u * u;
-          }
-        }
-        st_a = K + s1 * invC;
-        const float var = fmaxf(s2 - s1 * s1 * invC, 0.f) * invC1;
-        st_r = 1.f / sqrtf(var + 1e-5f);
-        if (valid && p.epi.ln_rstd_out) p.epi.ln_rstd_out[pix] = st_r;
-      } else if (ln == 2 && !(p.debug & 8)) {
-        float sg = 0.f, sga = 0.f;
-        for (int cc = 0; cc < p.out_chunks; ++cc) {
-          float g[32], a[32];
-          if (valid) {
-            const bf16* ah = a_pix + (size_t)cc * so.block_stride();
-            load32_hilo(ah, ah + so.lo_offset(), a);
-          }
-          tmem_ld32(t0 + cc * 32, g);
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              sg += g[j];
-              sga += g[j] * a[j];
-            }
-          }
-        }
-        st_a = sg * invC, st_b = sga * invC1;
-        st_r = valid ? p.epi.ln_rstd_in[pix] : 1.f;
       }
       for (int cc = cc0; cc < p.out_chunks; cc += ccstep) {
-        float v[32], f[32], rr[32], aa[32];
+        float v[32], f[32], rr[32];
         // operands from global memory first: their latency overlaps the accumulator load
         if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
         if (has_dact) load32(p.epi.dact + pix * p.Cout + cc * 32, rr);
-        if (ln == 2 && valid && !(p.debug & 16)) {
-          const bf16* ah = a_pix + (size_t)cc * so.block_stride();
-          load32_hilo(ah, ah + so.lo_offset(), aa);
-        }
         tmem_ld32(t0 + cc * 32, v);
         if (cc + ccstep >= p.out_chunks) {
           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
@@ -456,23 +409,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
               mbar_arrive(bar_tempty + 8 * acc);
           }
         }
-        if (ln == 2) {
-          // backward of the LayerNorm: gx = res + (g - mean g - a sum(g a)/(C-1)) rstd
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (v[j] - st_a - aa[j] * st_b) * st_r + (has_res ? rr[j] : 0.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = v[j];
-        } else {
-          epilogue_math32(p.epi, v, f, rr, has_res, has_dact, cc * 32);
-          if (ln == 1) {
-            float sh[32];
-            if (shiftp) load32_ldg(shiftp + cc * 32, sh);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (f[j] + (shiftp ? sh[j] : 0.f) - st_a) * st_r;
-          }
-        }
+        epilogue_math32(p.epi, v, f, rr, has_res, has_dact, cc * 32);
         if (p.debug & 32) continue;
         // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
         const uint32_t staging = staging0 + sbuf * kStagingBytes;
@@ -551,6 +488,289 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
   if (p.staged && threadIdx.x == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// ------------------------------------------------------------------------------------------ LayerNorm epilogue
+// Epilogue with the channel LayerNorm fused in (ConvEpilogue::ln: 1 forward, 2 adjoint), second generation.
+// The thread that owns a TMEM lane sees all C_out channels of its pixel, but not at once: the statistics need
+// one sweep over the channel blocks and the normalisation a second one.  What round 1 re-read from global
+// memory and recomputed in the second sweep now stays on chip:
+//   forward   f = acc + bias + res is written back IN PLACE of the accumulator (tcgen05.st) by the first sweep;
+//             the second sweep reads it from TMEM, normalises and stores.  One global read of `res`.
+//   adjoint   the saved operand a (hi + lo) is parked in the free TMEM columns behind the accumulator when
+//             there are any (C_out <= 128 double-buffered, <= 256 single), so the second sweep reads g and a
+//             from TMEM and only `res` from global memory.
+// Global operands are requested one channel block ahead (and the first block before the accumulator is waited
+// for), so their latency overlaps the TMEM traffic and the store staging of the previous block.
+// Single accumulator (C_out > 256, patch kernel): the two epilogue warpgroups split the channel blocks of every
+// tile (csplit) and exchange their partial statistics through shared memory (xchg) -- both warpgroups of a
+// pixel combine the two partials in the same order, so they normalise with identical numbers.
+template <int LN, bool CTA2>
+__device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
+                                                 uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
+                                                 uint32_t acc_stride, uint32_t staging_base, float2* xchg,
+                                                 int tile_begin, int tile_end, int warp, int lane, int wg, int nwg,
+                                                 bool csplit) {
+  const uint32_t staging0 = staging_base + wg * p.sbufs * kStagingBytes;
+  const int issuer = 64 + 128 * wg;
+  const int bar_id = wg;
+  const int half = wg;  // csplit: this warpgroup takes channel blocks half, half + 2, ...
+  const int cc0 = csplit ? wg : 0, ccstep = csplit ? nwg : 1;
+  if (csplit) wg = 0, nwg = 1;  // tile walk of a single warpgroup
+  const int q = warp & 3;
+  const int m = q * 32 + lane;
+  const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
+  const int C = p.Cout, nch = p.out_chunks;
+  const bool wantF = p.epi.outF != nullptr, wantO = p.epi.outOP != nullptr;
+  const OpShape so{0, p.Ho, p.Wo, C, 0};
+  const size_t bs = so.block_stride(), lo_off = so.lo_offset();
+  const float invC = 1.f / (float)C, invC1 = 1.f / (float)(C - 1);
+  const bool stash = LN == 2 && (p.acc_stages == 2 ? C <= 128 : C <= 256);
+  int it = wg;
+  int sbuf = 0;
+  for (int tile = tile_begin + wg * (int)gridDim.x; tile < tile_end; tile += nwg * (int)gridDim.x, it += nwg) {
+    const int acc = it % p.acc_stages;
+    const uint32_t acc_phase = (it / p.acc_stages) & 1;
+    int n0, h0, w0;
+    p.g.tile_origin(tile, n0, h0, w0);
+    const int n = n0 + bn, h = p.os * (h0 + bh) + p.oh0, w = p.os * (w0 + bw) + p.ow0;
+    const bool valid = n < p.N;
+    const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+    const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
+    const bool has_res = p.epi.res != nullptr && valid;
+    const float* resp = p.epi.res + pix * C;
+    const bf16* a_pix = (LN == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
+    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
+    const uint32_t ts = t0 + (uint32_t)C;  // stash columns (adjoint)
+    {
+      // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
+      const int nt = tile + nwg * (int)gridDim.x;
+      if (nt < p.g.num_tiles) {
+        int nn0, nh0, nw0;
+        p.g.tile_origin(nt, nn0, nh0, nw0);
+        const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
+        if (nn < p.N) {
+          const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
+          if (p.epi.res)
+            for (int c = cc0; c < nch; c += ccstep) prefetch_l2(p.epi.res + npix * C + c * 32);
+          if (LN == 2) {
+            const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
+            for (int c = cc0; c < nch; c += ccstep) {
+              prefetch_l2(pa + (size_t)c * bs);
+              prefetch_l2(pa + (size_t)c * bs + lo_off);
+            }
+          }
+        }
+      }
+    }
+
+    // output of one 32-channel block through the staging tiles: F <- v (fp32), then OP <- post(v) (bf16 hi / lo)
+    auto stage_and_store = [&](int cc, float (&v)[32], auto&& post) {
+      const uint32_t staging = staging0 + sbuf * kStagingBytes;
+      if (threadIdx.x == issuer) {
+        if (p.sbufs == 1)
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else if (p.sbufs == 2)
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else
+          asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+      }
+      EPI_BARRIER();
+      if (wantF) {
+        const uint32_t row = staging + m * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          st_shared_v4(row + ((j ^ (m & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+      }
+      post(v);
+      if (wantO) {
+        uint32_t ph[16], pl[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], ph[j], pl[j]);
+        const uint32_t rh = staging + kStageF + m * 64, rl = rh + kStageO;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t sw = (j ^ ((m >> 1) & 3)) << 4;
+          st_shared_v4(rh + sw, ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+          st_shared_v4(rl + sw, pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+        }
+        if (edge) {
+          // halo replicas of edge pixels (the TMA box covers the interior position only)
+          const size_t blk = (size_t)cc * bs;
+          bool first = true;
+          for_each_replica(h, w, p.Ho, p.Wo, [&](int hp, int wp) {
+            if (first) {
+              first = false;
+              return;
+            }
+            bf16* dst = p.epi.outOP + op_offset(so, n, hp, wp) + blk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<uint4*>(dst)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+              reinterpret_cast<uint4*>(dst + lo_off)[j] =
+                  make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+            }
+          });
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      EPI_BARRIER();
+      if (threadIdx.x == issuer) {
+        if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
+        if (wantO) {
+          tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
+          tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0);
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (++sbuf == p.sbufs) sbuf = 0;
+    };
+    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
+    auto release_acc = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CTA2)
+          mbar_arrive_leader(bar_tempty + 8 * acc);
+        else
+          mbar_arrive(bar_tempty + 8 * acc);
+      }
+    };
+    // partial statistics of the two warpgroups of a csplit tile -> both partials, in warpgroup order
+    auto exchange = [&](float a, float b, float2& p0, float2& p1) {
+      float2* slot = xchg + (size_t)((it & 1) * 2) * 128;
+      slot[half * 128 + m] = make_float2(a, b);
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      const float2 other = slot[(half ^ 1) * 128 + m];
+      p0 = half == 0 ? make_float2(a, b) : other;
+      p1 = half == 0 ? other : make_float2(a, b);
+    };
+
+    if constexpr (LN == 1) {
+      const float* shiftp =
+          p.epi.ln_shift ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride : nullptr;
+      float rr[32];
+      if (has_res) load32(resp + cc0 * 32, rr);
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      // ---- first sweep: f = acc + bias + res back into TMEM; shifted one-pass statistics of f + shift
+      float s1 = 0.f, s2 = 0.f, K = 0.f;
+      for (int cc = cc0; cc < nch; cc += ccstep) {
+        float f[32];
+        tmem_ld32(t0 + cc * 32, f);
+        if (p.epi.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.epi.bias + cc * 32 + j));
+            f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+          }
+        }
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += rr[j];
+          // consumed: request the next block's residual, it arrives while this block is finished
+          if (cc + ccstep < nch) load32(resp + (cc + ccstep) * 32, rr);
+        }
+        tmem_st32(t0 + cc * 32, f);
+        if (cc == cc0) K = f[0] + (shiftp ? __ldg(shiftp + cc * 32) : 0.f);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (shiftp) sh = __ldg(reinterpret_cast<const float4*>(shiftp + cc * 32 + j));
+          const float d0 = f[j] + sh.x - K, d1 = f[j + 1] + sh.y - K, d2 = f[j + 2] + sh.z - K,
+                      d3 = f[j + 3] + sh.w - K;
+          s1 += d0, s2 += d0 * d0;
+          s1 += d1, s2 += d1 * d1;
+          s1 += d2, s2 += d2 * d2;
+          s1 += d3, s2 += d3 * d3;
+        }
+      }
+      float mean, m2;
+      if (!csplit) {
+        mean = K + s1 * invC;
+        m2 = fmaxf(s2 - s1 * s1 * invC, 0.f);
+      } else {
+        const float cnt = (float)(32 * ((nch - cc0 + ccstep - 1) / ccstep));
+        float2 p0, p1;
+        exchange(K + s1 / cnt, fmaxf(s2 - s1 * s1 / cnt, 0.f), p0, p1);
+        const float c0n = (float)(32 * ((nch + 1) / 2)), c1n = (float)(32 * (nch / 2));
+        const float dm = p1.x - p0.x;
+        mean = (c0n * p0.x + c1n * p1.x) * invC;
+        m2 = p0.y + p1.y + dm * dm * (c0n * c1n * invC);
+      }
+      const float rstd = 1.f / sqrtf(m2 * invC1 + 1e-5f);
+      if (valid && p.epi.ln_rstd_out && (!csplit || half == 0)) p.epi.ln_rstd_out[pix] = rstd;
+      tmem_st_wait();
+      // ---- second sweep: F <- f, OP <- (f + shift - mean) rstd
+      for (int cc = cc0; cc < nch; cc += ccstep) {
+        float f[32];
+        tmem_ld32(t0 + cc * 32, f);
+        if (cc + ccstep >= nch) release_acc();
+        stage_and_store(cc, f, [&](float (&v)[32]) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (shiftp) sh = __ldg(reinterpret_cast<const float4*>(shiftp + cc * 32 + j));
+            v[j] = (v[j] + sh.x - mean) * rstd, v[j + 1] = (v[j + 1] + sh.y - mean) * rstd;
+            v[j + 2] = (v[j + 2] + sh.z - mean) * rstd, v[j + 3] = (v[j + 3] + sh.w - mean) * rstd;
+          }
+        });
+      }
+    } else {
+      // ---- adjoint: gx = res + (g - mean_C g - a sum_C(g a) / (C - 1)) rstd
+      float aa[32];
+      if (valid) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
+      const float rstd = valid ? p.epi.ln_rstd_in[pix] : 1.f;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      float sg = 0.f, sga = 0.f;
+      for (int cc = cc0; cc < nch; cc += ccstep) {
+        float g[32];
+        tmem_ld32(t0 + cc * 32, g);
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            sg += g[j];
+            sga += g[j] * aa[j];
+          }
+        }
+        if (stash) tmem_st32(ts + cc * 32, aa);
+        // consumed: request the next block of a, it arrives during the next accumulator load
+        if (valid && cc + ccstep < nch) {
+          const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
+          load32_hilo(an, an + lo_off, aa);
+        }
+      }
+      float rr[32];
+      if (has_res) load32(resp + cc0 * 32, rr);
+      if (csplit) {
+        float2 p0, p1;
+        exchange(sg, sga, p0, p1);
+        sg = p0.x + p1.x, sga = p0.y + p1.y;
+      }
+      const float mg = sg * invC, beta = sga * invC1;
+      if (stash) tmem_st_wait();
+      for (int cc = cc0; cc < nch; cc += ccstep) {
+        float g[32], a[32];
+        if (!stash && valid) {
+          const bf16* ac = a_pix + (size_t)cc * bs;
+          load32_hilo(ac, ac + lo_off, a);
+        }
+        tmem_ld32(t0 + cc * 32, g);
+        if (stash) tmem_ld32(ts + cc * 32, a);
+        if (cc + ccstep >= nch) release_acc();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) g[j] = (g[j] - mg - a[j] * beta) * rstd + (has_res ? rr[j] : 0.f);
+        }
+        // the residual of this block is consumed: request the next block's while this one is staged
+        if (has_res && cc + ccstep < nch) load32(resp + (cc + ccstep) * 32, rr);
+        stage_and_store(cc, g, [](float (&)[32]) {});
+      }
+    }
+  }
+  if (threadIdx.x == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 // One lane of the (converged) warp; the compiler keeps the guarded block on the uniform datapath.
 __device__ __forceinline__ bool elect_one() {
@@ -591,7 +811,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t bar_tfull = base + 128;     // 2 x 8 B
   const uint32_t bar_tempty = base + 144;    // 2 x 8 B
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 160);
-  const uint32_t staging0 = base + kCtrlBytes;            // sbufs x [F 16 KB][hi 8 KB][lo 8 KB]
+  const uint32_t staging0 = base + p.ctrl_bytes;          // sbufs x [F 16 KB][hi 8 KB][lo 8 KB]
   const uint32_t stage0 = staging0 + p.sbufs * kStagingBytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -747,8 +967,12 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
-    epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
-                            warp, lane);
+    if constexpr (LN != 0)
+      epilogue_ln_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, nullptr,
+                                 tile_begin, tile_end, warp, lane, 0, 1, false);
+    else
+      epilogue_role<CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
+                          warp, lane);
   }
 
   __syncwarp();
@@ -789,7 +1013,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const uint32_t bar_tfull = base + 320;      // 2 x 8 B
   const uint32_t bar_tempty = base + 336;     // 2 x 8 B
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 352);
-  const uint32_t staging0 = base + kCtrlBytes;
+  const uint32_t staging0 = base + p.ctrl_bytes;
   const uint32_t aring0 = staging0 + 2 * p.sbufs * kStagingBytes;  // one staging set per epilogue warpgroup
   constexpr uint32_t a_stage_bytes = PLANES * kPatchPlane;
   const uint32_t bring0 = aring0 + p.a_stages * a_stage_bytes;
@@ -800,8 +1024,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const bool leader = rank == 0;
   const int tile_begin = CTA2 ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
   const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
-  // single accumulator (C_out > 256), no LayerNorm: the two epilogue warpgroups split every tile's channel blocks
-  const bool csplit = LN == 0 && (p.acc_stages == 1 || p.csplit) && blockDim.x == kPatchThreads;
+  // single accumulator (C_out > 256): the two epilogue warpgroups split every tile's channel blocks (with a fused
+  // LayerNorm they exchange their partial statistics, epilogue_ln_role)
+  const bool csplit = (p.acc_stages == 1 || (LN == 0 && p.csplit)) && blockDim.x == kPatchThreads;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -964,9 +1189,15 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     // ===================================================================== epilogue (warps 2..5, 6..9)
     // with a double-buffered accumulator the two warpgroups take alternate tiles
     const int wg = (warp - 2) >> 2, nwg = ((p.acc_stages == 2 || csplit) && blockDim.x == kPatchThreads) ? 2 : 1;
-    if (wg < nwg)
-      epilogue_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin,
-                              tile_end, warp, lane, wg, nwg, csplit);
+    if (wg < nwg) {
+      if constexpr (LN != 0)
+        epilogue_ln_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0,
+                                   reinterpret_cast<float2*>(base_ptr + kCtrlBytes), tile_begin, tile_end, warp, lane,
+                                   wg, nwg, csplit);
+      else
+        epilogue_role<CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
+                            warp, lane, wg, nwg, csplit);
+    }
   }
 
   __syncwarp();
@@ -1066,6 +1297,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(!c.epi.ln || p.staged, "the fused LayerNorm epilogue needs C_out % 32 == 0");
   SDAB_REQUIRE(c.epi.ln != 2 || (c.epi.ln_a && c.epi.ln_rstd_in && !c.epi.bias && !c.epi.act && !c.epi.dact),
                "invalid backward-LayerNorm epilogue");
+  p.ctrl_bytes = kCtrlBytes;
   p.sbufs = 1;  // measured: deeper store staging does not pay for the ring stages it costs
   if (getenv("SDAB_UMMA_SBUFS")) p.sbufs = atoi(getenv("SDAB_UMMA_SBUFS"));
   SDAB_REQUIRE(p.sbufs >= 1 && p.sbufs <= 3, "staging sets out of range");
@@ -1075,6 +1307,8 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
   static const int csplit_env = getenv("SDAB_UMMA_CSPLIT") ? atoi(getenv("SDAB_UMMA_CSPLIT")) : 0;
   p.csplit = csplit_env;
+  SDAB_REQUIRE(c.epi.ln != 1 || (!c.epi.act && !c.epi.dact && !c.epi.pre),
+               "the fused forward LayerNorm follows a plain (bias / residual) convolution");
   p.patch = patch_env && cta2 && p.staged && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 && p.os == 1 &&
             c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
   if (p.patch) {
@@ -1082,7 +1316,9 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     p.g.tiles_w = c.W / kPatchBW, p.g.tiles_h = c.H / kPatchBH, p.g.tiles_n = c.N;
     p.g.num_tiles = p.g.tiles_w * p.g.tiles_h * p.g.tiles_n;
     p.b_stage_bytes = p.planes * p.b_plane_bytes;
-    const uint32_t fixed = kCtrlBytes + 1024 + 2 * p.sbufs * kStagingBytes;
+    // csplit statistics exchange of the LayerNorm epilogue: 2 tile parities x 2 warpgroups x 128 pixels x float2
+    if (c.epi.ln && p.acc_stages == 1 && patch_wg == 2) p.ctrl_bytes += 4096;
+    const uint32_t fixed = p.ctrl_bytes + 1024 + 2 * p.sbufs * kStagingBytes;
     p.a_stages = 3;
     p.stages = (int)((kSmemBudget - fixed - p.a_stages * p.planes * kPatchPlane) / p.b_stage_bytes);
     if (p.stages < 4) {
@@ -1092,7 +1328,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     if (p.stages > kMaxBStages) p.stages = kMaxBStages;
     SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
   } else {
-    p.stages = (int)((kSmemBudget - kCtrlBytes - 1024 - p.sbufs * kStagingBytes) / p.stage_bytes);
+    p.stages = (int)((kSmemBudget - p.ctrl_bytes - 1024 - p.sbufs * kStagingBytes) / p.stage_bytes);
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     SDAB_REQUIRE(p.stages >= 2, "convolution does not fit the shared-memory pipeline");
   }
@@ -1150,7 +1386,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     SDAB_TRY(encode(&tmO, basep, 5, dims, strides, box));
   }
 
-  const size_t smem = kCtrlBytes + 1024 + (size_t)(p.patch ? 2 : 1) * p.sbufs * kStagingBytes +
+  const size_t smem = p.ctrl_bytes + 1024 + (size_t)(p.patch ? 2 : 1) * p.sbufs * kStagingBytes +
                       (p.patch ? (size_t)p.a_stages * p.planes * kPatchPlane + (size_t)p.stages * p.b_stage_bytes
                                : (size_t)p.stages * p.stage_bytes);
   using Kernel = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, UmmaParams);
