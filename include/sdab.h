@@ -103,6 +103,29 @@ size_t sdab_unet_workspace_bytes(const sdab_unet* h, int N, int H, int W, int sa
 int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
                       void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream);
 
+/* MCScoreNet.forward (score.py:134-144) for the windows [w_begin, w_end) of the flattened (B, L - 2k) window
+ * index, with unfold (score.py:146-153), ScoreUNet.forward's context concat (score.py:87) and fold
+ * (score.py:155-164) as ADDRESSING of the network's first and last layer instead of tensors:
+ *   x   : the trajectory (B, L, C, H, W); window i of trajectory b is frames i .. i + 2k;
+ *   ctx : (Cc, H, W) context planes appended to every window (NULL when Cc == 0);
+ *   y   : (1, mod_features) modulation vector (one diffusion time per call);
+ *   out : cap == 0 -- the score (B, L, C, H, W); the call writes the frames its windows feed (the centre
+ *         slot of every window, the k leading / trailing slots of the first / last window of a trajectory);
+ *         cap  > 0 -- this rank's shard of `cap` frames (C, H, W): the centre frame of local window n at
+ *         position n, the 2k edge frames of the j-th trajectory the range touches at per + 2k j + e.
+ *         Equal-size shards are what one all-gather moves; sdab_frames_assemble builds the score from them.
+ * The network must have in_channels = (2k+1) C + Cc and out_channels = (2k+1) C.  Workspace as for
+ * sdab_unet_forward with N = w_end - w_begin. */
+int sdab_mcscore_forward(sdab_unet* h, const float* x, const float* ctx, const float* y, int B, int L, int C, int Cc,
+                         int H, int W, int order, int w_begin, int w_end, float* out, int per, int cap,
+                         void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream);
+/* Input-VJP of the last sdab_mcscore_forward(save != 0): gs is the cotangent of the folded score
+ * (B, L, C, H, W); gwin receives the window input-gradients (w_end - w_begin, (2k+1) C, H, W) (the cotangent
+ * of the unfolded windows, context channels dropped) -- sdab_unfold_transpose_add overlap-adds them. */
+int sdab_mcscore_dgrad(sdab_unet* h, const float* gs, float* gwin, int B, int L, int C, int Cc, int H, int W, int order,
+                       int w_begin, int w_end, void* workspace, size_t workspace_bytes, int mode, int engine,
+                       void* stream);
+
 /* Vector-Jacobian product w.r.t. x of the last forward run with save != 0 on the
  * same workspace: gx = J_x^T gout (what torch.autograd.grad does through the
  * reference UNet in GaussianScore.forward, score.py:381-394). */
@@ -154,6 +177,10 @@ int sdab_unfold_cat(const float* x, const float* ctx, float* win, int B, int L, 
 int sdab_fold(const float* win_out, float* s, int B, int L, int C, int H, int W, int order, void* stream);
 /* adjoint of fold: scatter of the cotangent into zero-initialised windows */
 int sdab_fold_transpose(const float* gs, float* gwin, int B, int L, int C, int H, int W, int order, void* stream);
+/* Builds the score (B, L, C, H, W) from the all-gathered shards of sdab_mcscore_forward(cap > 0):
+ * gathered: (world * cap, C, H, W), rank r's shard at r * cap; rank r owns windows [r per, (r+1) per). */
+int sdab_frames_assemble(const float* gathered, float* s, int B, int L, int C, int H, int W, int order, int per, int cap,
+                         void* stream);
 /* adjoint of unfold_cat w.r.t. x: deterministic overlap-add (autograd UnfoldBackward0) */
 int sdab_unfold_transpose_add(const float* gwin, float* gx, int B, int L, int C, int Cc, int H, int W, int order,
                               void* stream);

@@ -56,6 +56,10 @@ _PROTOTYPES = {
     'sdab_unet_backward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int,
                                    c_int, c_void_p]),
     'sdab_unet_shift_rows': (c_int, [c_void_p]),
+    'sdab_mcscore_forward': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    'sdab_mcscore_dgrad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_int, c_void_p, c_size_t, c_int, c_int, c_void_p]),
     'sdab_conv3x3_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
     'sdab_conv3x3': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_int, c_void_p, c_size_t, c_void_p]),
@@ -63,6 +67,7 @@ _PROTOTYPES = {
     'sdab_unfold_cat': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'sdab_fold': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'sdab_fold_transpose': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    'sdab_frames_assemble': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'sdab_unfold_transpose_add': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     # sampler
     'sdab_vpsde_predict': (c_int, [c_void_p, c_void_p, c_float, c_float, c_size_t, c_void_p]),

@@ -287,6 +287,18 @@ __device__ __forceinline__ void epilogue_store16(const ConvEpilogue& e, float (&
 }
 
 // ----------------------------------------------------------------------------- elementwise launches
+// Window view of a trajectory (MCScoreNet.forward, sda/score.py:134-164): the range of flattened (B, L - 2k)
+// windows one call evaluates, and where the folded frames go (FoldDst in elementwise.cu).
+struct WindowIO {
+  int B, L, C, Cc;  // trajectory (B, L, C, H, W); context channels appended to every window
+  int order;        // k: a window is 2k + 1 frames
+  int w_begin;      // first flattened window of this call
+  int per, cap;     // sharded output: windows per rank and frames per shard; cap == 0: write the trajectory in place
+};
+int pack_windows_to_op(const float* x, const float* ctx, bf16* op, const WindowIO& w, int N, int Cpad, int H, int W,
+                       cudaStream_t st);
+int pack_fold_adjoint_to_op(const float* g, bf16* op, const WindowIO& w, int N, int Cpad, int H, int W, cudaStream_t st);
+int unpack_f_fold(const float* f, float* out, const WindowIO& w, int N, int Cpad, int H, int W, cudaStream_t st);
 int pack_nchw_to_op(const float* x, bf16* op, int N, int Creal, int Cpad, int H, int W, int s2, cudaStream_t st);
 int unpack_f_to_nchw(const float* f, float* x, int N, int Creal, int Cpad, int H, int W, cudaStream_t st);
 // kind: 0 normal, 1 S2 (parity) layout, 2 zero-insertion x2 upsample (src at half resolution)

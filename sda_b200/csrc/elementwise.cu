@@ -21,11 +21,59 @@ __device__ __forceinline__ float warp_sum(float v) {
 inline dim3 warp_grid(size_t n_warps) { return dim3((unsigned)((n_warps + kWarpsPerBlock - 1) / kWarpsPerBlock)); }
 
 // ---------------------------------------------------------------------------------------------
-// NCHW fp32 -> OP(Cpad): the entry of the network.  ScoreUNet.forward hands the U-Net a
-// contiguous (N, C, H, W) tensor (sda/score.py:89-93).  Tile of 32 pixels along W through smem.
+// Planar fp32 images -> OP(Cpad): the entry of the network.  `Src::plane(n, c)` is the H x W plane that
+// holds channel c of image n, or null for a zero channel:
+//   NchwSrc       a contiguous (N, C, H, W) tensor, as ScoreUNet.forward hands the U-Net (sda/score.py:89-93);
+//   WindowSrc     MCScoreNet.unfold + the context concat as addressing (sda/score.py:87,146-153): window i of
+//                 trajectory b is the contiguous slab of frames i .. i + 2k, the context planes follow;
+//   FoldAdjSrc    the adjoint of MCScoreNet.fold (sda/score.py:157-164) as addressing: slot s of window i holds
+//                 the cotangent of frame j when (i, s) feeds j, and zero otherwise.
+// Tile of 32 pixels along W through smem.
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_nchw_kernel(const float* __restrict__ x, bf16* __restrict__ op, int N, int Creal, int Cpad, int H,
-                                 int W, int s2) {
+struct NchwSrc {
+  const float* x;
+  int C;
+  size_t HW;
+  __device__ __forceinline__ const float* plane(int n, int c) const {
+    return c < C ? x + ((size_t)n * C + c) * HW : nullptr;
+  }
+};
+
+struct WindowSrc {
+  const float* x;    // (B, L, C, H, W)
+  const float* ctx;  // (Cc, H, W) or null
+  WindowIO w;
+  size_t HW;
+  __device__ __forceinline__ const float* plane(int n, int c) const {
+    const int nw = w.L - 2 * w.order, cw = (2 * w.order + 1) * w.C;
+    const int wi = w.w_begin + n, b = wi / nw, i = wi % nw;
+    if (c < cw) return x + (((size_t)b * w.L + i) * w.C + c) * HW;
+    if (c < cw + w.Cc) return ctx + (size_t)(c - cw) * HW;
+    return nullptr;
+  }
+};
+
+struct FoldAdjSrc {
+  const float* g;  // (B, L, C, H, W)
+  WindowIO w;
+  size_t HW;
+  __device__ __forceinline__ const float* plane(int n, int c) const {
+    const int k = w.order, nw = w.L - 2 * k;
+    if (c >= (2 * k + 1) * w.C) return nullptr;
+    const int wi = w.w_begin + n, b = wi / nw, i = wi % nw, slot = c / w.C, ch = c % w.C;
+    int j = -1;
+    if (slot == k)
+      j = i + k;
+    else if (i == 0 && slot < k)
+      j = slot;
+    else if (i == nw - 1 && slot > k)
+      j = nw - 1 + slot;
+    return j >= 0 ? g + (((size_t)b * w.L + j) * w.C + ch) * HW : nullptr;
+  }
+};
+
+template <class Src>
+__global__ void pack_planes_kernel(const Src src, bf16* __restrict__ op, int N, int Cpad, int H, int W, int s2) {
   __shared__ float tile[kChanTile][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
@@ -35,7 +83,8 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, bf16* __restrict__
     __syncthreads();
     for (int c = ty; c < nc; c += blockDim.y) {
       float v = 0.f;
-      if (cb + c < Creal && w0 + tx < W) v = x[(((size_t)n * Creal + cb + c) * H + h) * W + w0 + tx];
+      const float* pl = src.plane(n, cb + c);
+      if (pl && w0 + tx < W) v = pl[(size_t)h * W + w0 + tx];
       tile[c][tx] = v;
     }
     __syncthreads();
@@ -56,9 +105,45 @@ __global__ void pack_nchw_kernel(const float* __restrict__ x, bf16* __restrict__
   }
 }
 
-// F(Cpad) -> NCHW fp32 (first Creal channels): the exit of the network.
-__global__ void unpack_nchw_kernel(const float* __restrict__ f, float* __restrict__ x, int N, int Creal, int Cpad,
-                                   int H, int W) {
+// F(Cpad) -> planar fp32 images: the exit of the network.  `Dst::plane(n, c)` is the destination plane of
+// channel c of image n, or null when that channel is dropped:
+//   NchwDst    a contiguous (N, Creal, H, W) tensor;
+//   FoldDst    MCScoreNet.fold as addressing (sda/score.py:157-164): only the centre slot of every window and
+//              the side slots of the first / last window of a trajectory are kept; the frames land either at
+//              their place in the (B, L, C, H, W) score (cap == 0) or in this rank's shard of `cap` frames
+//              (centre frames first, then 2k edge frames per trajectory the rank touches; sdab_frames_assemble).
+struct NchwDst {
+  float* x;
+  int C;
+  size_t HW;
+  __device__ __forceinline__ float* plane(int n, int c) const { return c < C ? x + ((size_t)n * C + c) * HW : nullptr; }
+};
+
+struct FoldDst {
+  float* out;
+  WindowIO w;
+  size_t HW;
+  __device__ __forceinline__ float* plane(int n, int c) const {
+    const int k = w.order, nw = w.L - 2 * k;
+    if (c >= (2 * k + 1) * w.C) return nullptr;
+    const int wi = w.w_begin + n, b = wi / nw, i = wi % nw, slot = c / w.C, ch = c % w.C;
+    int j = -1;
+    if (slot == k)
+      j = i + k;
+    else if (i == 0 && slot < k)
+      j = slot;
+    else if (i == nw - 1 && slot > k)
+      j = nw - 1 + slot;
+    if (j < 0) return nullptr;
+    if (w.cap == 0) return out + (((size_t)b * w.L + j) * w.C + ch) * HW;
+    const int pos = slot == k ? n : w.per + (b - w.w_begin / nw) * 2 * k + (slot < k ? slot : slot - 1);
+    return out + ((size_t)pos * w.C + ch) * HW;
+  }
+};
+
+template <class Dst>
+__global__ void unpack_planes_kernel(const float* __restrict__ f, const Dst dst, int N, int Creal, int Cpad, int H,
+                                     int W) {
   __shared__ float tile[kChanTile][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
@@ -71,8 +156,10 @@ __global__ void unpack_nchw_kernel(const float* __restrict__ f, float* __restric
       for (int c = tx; c < nc; c += 32) tile[c][px] = f[(((size_t)n * H + h) * W + w) * Cpad + cb + c];
     }
     __syncthreads();
-    for (int c = ty; c < nc && cb + c < Creal; c += blockDim.y)
-      if (w0 + tx < W) x[(((size_t)n * Creal + cb + c) * H + h) * W + w0 + tx] = tile[c][tx];
+    for (int c = ty; c < nc && cb + c < Creal; c += blockDim.y) {
+      float* pl = dst.plane(n, cb + c);
+      if (pl && w0 + tx < W) pl[(size_t)h * W + w0 + tx] = tile[c][tx];
+    }
   }
 }
 
@@ -398,15 +485,39 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
 
 int pack_nchw_to_op(const float* x, bf16* op, int N, int Creal, int Cpad, int H, int W, int s2, cudaStream_t st) {
   dim3 grid((W + 31) / 32, H, N), block(32, 8);
-  pack_nchw_kernel<<<grid, block, 0, st>>>(x, op, N, Creal, Cpad, H, W, s2);
-  SDAB_LAUNCH_CHECK("pack_nchw_kernel");
+  pack_planes_kernel<<<grid, block, 0, st>>>(NchwSrc{x, Creal, (size_t)H * W}, op, N, Cpad, H, W, s2);
+  SDAB_LAUNCH_CHECK("pack_planes_kernel");
+  return SDAB_OK;
+}
+
+int pack_windows_to_op(const float* x, const float* ctx, bf16* op, const WindowIO& w, int N, int Cpad, int H, int W,
+                       cudaStream_t st) {
+  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  pack_planes_kernel<<<grid, block, 0, st>>>(WindowSrc{x, ctx, w, (size_t)H * W}, op, N, Cpad, H, W, 0);
+  SDAB_LAUNCH_CHECK("pack_planes_kernel");
+  return SDAB_OK;
+}
+
+int pack_fold_adjoint_to_op(const float* g, bf16* op, const WindowIO& w, int N, int Cpad, int H, int W,
+                            cudaStream_t st) {
+  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  pack_planes_kernel<<<grid, block, 0, st>>>(FoldAdjSrc{g, w, (size_t)H * W}, op, N, Cpad, H, W, 0);
+  SDAB_LAUNCH_CHECK("pack_planes_kernel");
   return SDAB_OK;
 }
 
 int unpack_f_to_nchw(const float* f, float* x, int N, int Creal, int Cpad, int H, int W, cudaStream_t st) {
   dim3 grid((W + 31) / 32, H, N), block(32, 8);
-  unpack_nchw_kernel<<<grid, block, 0, st>>>(f, x, N, Creal, Cpad, H, W);
-  SDAB_LAUNCH_CHECK("unpack_nchw_kernel");
+  unpack_planes_kernel<<<grid, block, 0, st>>>(f, NchwDst{x, Creal, (size_t)H * W}, N, Creal, Cpad, H, W);
+  SDAB_LAUNCH_CHECK("unpack_planes_kernel");
+  return SDAB_OK;
+}
+
+int unpack_f_fold(const float* f, float* out, const WindowIO& w, int N, int Cpad, int H, int W, cudaStream_t st) {
+  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  unpack_planes_kernel<<<grid, block, 0, st>>>(f, FoldDst{out, w, (size_t)H * W}, N, (2 * w.order + 1) * w.C, Cpad, H,
+                                               W);
+  SDAB_LAUNCH_CHECK("unpack_planes_kernel");
   return SDAB_OK;
 }
 

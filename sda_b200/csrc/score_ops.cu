@@ -117,6 +117,26 @@ __global__ void unfold_transpose_kernel(const float* __restrict__ gwin, float* _
   }
 }
 
+// score frame (b, f) <- its position in the gathered shards of the window-sharded evaluation (FoldDst, elementwise.cu)
+__global__ void frames_assemble_kernel(const float4* __restrict__ gathered, float4* __restrict__ s, int B, int L, int k,
+                                       size_t frame4, int per, int cap) {
+  const int nw = L - 2 * k;
+  const int frame = blockIdx.y, b = frame / L, f = frame % L;
+  const int wi = b * nw + min(max(f - k, 0), nw - 1);
+  const int r = wi / per, j = wi - r * per;
+  int pos;
+  if (f >= k && f < L - k) {
+    pos = r * cap + j;
+  } else {
+    const int e = f < k ? f : k + (f - (L - k));
+    pos = r * cap + per + (b - (r * per) / nw) * 2 * k + e;
+  }
+  const float4* src = gathered + (size_t)pos * frame4;
+  float4* dst = s + (size_t)frame * frame4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < frame4; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
 // ------------------------------------------------------------------------------- Philox4x32-10
 struct Philox {
   uint32_t k0, k1;
@@ -312,6 +332,20 @@ int sdab_unfold_transpose_add(const float* gwin, float* gx, int B, int L, int C,
   unfold_transpose_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)stream>>>(gwin, gx, B, L, C, Cc, (size_t)H * W,
                                                                                order);
   SDAB_LAUNCH_CHECK("unfold_transpose_kernel");
+  return SDAB_OK;
+}
+
+int sdab_frames_assemble(const float* gathered, float* s, int B, int L, int C, int H, int W, int order, int per, int cap,
+                         void* stream) {
+  SDAB_REQUIRE(gathered && s, "null argument");
+  SDAB_REQUIRE(order >= 1 && L >= 2 * order + 1 && per >= 1 && cap >= per, "invalid shard geometry");
+  SDAB_REQUIRE(((size_t)C * H * W) % 4 == 0, "frame size must be a multiple of 4 floats");
+  SDAB_TRY(sdab_device_check());
+  const size_t frame4 = (size_t)C * H * W / 4;
+  const int gx = (int)((frame4 + kBlock - 1) / kBlock < 32 ? (frame4 + kBlock - 1) / kBlock : 32);
+  frames_assemble_kernel<<<dim3(gx, B * L), kBlock, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(gathered), reinterpret_cast<float4*>(s), B, L, order, frame4, per, cap);
+  SDAB_LAUNCH_CHECK("frames_assemble_kernel");
   return SDAB_OK;
 }
 

@@ -286,8 +286,15 @@ size_t sdab_unet_workspace_bytes(const sdab_unet* h, int N, int H, int W, int sa
   return make_plan(h, N, N, H, W, save != 0, save == 2).total;
 }
 
-int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
-                      void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// wio != null: x is the trajectory (B, L, C, H, W) and ctx the context planes; the network input is the window
+// batch [w_begin, w_begin + N) by addressing, and `out` receives the folded frames (WindowIO, common.cuh)
+int forward_impl(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
+                 void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream,
+                 const WindowIO* wio, const float* ctx) {
   SDAB_REQUIRE(h && x && y && out && workspace, "null argument");
   if (!h->weights_set) return fail(SDAB_ERR_STATE, "sdab_unet_set_weights has not been called");
   SDAB_REQUIRE(Nt == 1 || Nt == N, "the modulation batch must be 1 or N");
@@ -311,7 +318,10 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
   h->saved = false;
 
   const int kin0 = round_up(h->d.in_channels, 32);
-  SDAB_TRY(pack_nchw_to_op(x, OP(p.in_op), N, h->d.in_channels, kin0, H, W, 0, st));
+  if (wio)
+    SDAB_TRY(pack_windows_to_op(x, ctx, OP(p.in_op), *wio, N, kin0, H, W, st));
+  else
+    SDAB_TRY(pack_nchw_to_op(x, OP(p.in_op), N, h->d.in_channels, kin0, H, W, 0, st));
   SDAB_TRY(time_shifts(y, (const float*)(pk + h->off_projw), (const float*)(pk + h->off_projb), F(p.shift), Nt,
                        h->shift_rows, h->d.mod_features, st));
 
@@ -444,7 +454,10 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
       q.in = OP(p.finop), q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = C, q.Cout = h->convs[ci].nf;
       q.stride = 1, q.mode = mode, q.epi.bias = bias(ci), q.epi.outF = F(p.outf);
       SDAB_TRY(run_conv(engine, q, st, -1, h->d.out_channels));
-      SDAB_TRY(unpack_f_to_nchw(F(p.outf), out, N, h->d.out_channels, h->convs[ci].nf, Hd, Wd, st));
+      if (wio)
+        SDAB_TRY(unpack_f_fold(F(p.outf), out, *wio, N, h->convs[ci].nf, Hd, Wd, st));
+      else
+        SDAB_TRY(unpack_f_to_nchw(F(p.outf), out, N, h->d.out_channels, h->convs[ci].nf, Hd, Wd, st));
     }
   }
   if (save) {
@@ -454,10 +467,6 @@ int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int 
   return SDAB_OK;
 }
 
-}  // extern "C"
-
-namespace {
-
 // parameter-gradient targets of the training backward (host arrays of device pointers)
 struct WTargets {
   float* const* dw;
@@ -465,8 +474,10 @@ struct WTargets {
   float* dshift;
 };
 
+// wio != null: gout is the cotangent of the FOLDED score (B, L, C, H, W) (the adjoint of fold is addressing) and gx
+// receives the window input-gradients (N, (2k+1) C, H, W) without the context channels
 int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
-                  int engine, void* stream, const WTargets* wt) {
+                  int engine, void* stream, const WTargets* wt, const WindowIO* wio = nullptr) {
   SDAB_REQUIRE(h && gout && gx && workspace, "null argument");
   if (!h->saved || h->sws != workspace)
     return fail(SDAB_ERR_STATE, "the backward pass needs a preceding sdab_unet_forward(save != 0) on the same workspace");
@@ -604,7 +615,10 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
   };
 
   const int kout = round_up(h->d.out_channels, 32);
-  SDAB_TRY(pack_nchw_to_op(gout, OP(p.gout_op), N, h->d.out_channels, kout, H, W, 0, st));
+  if (wio)
+    SDAB_TRY(pack_fold_adjoint_to_op(gout, OP(p.gout_op), *wio, N, kout, H, W, st));
+  else
+    SDAB_TRY(pack_nchw_to_op(gout, OP(p.gout_op), N, h->d.out_channels, kout, H, W, 0, st));
   const float* cur;
   {
     const int ci = h->tail_conv[0];
@@ -709,15 +723,52 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
       q.in = GOP(0), q.wpk = wb(ci), q.N = N, q.H = H, q.W = W, q.Cin = C, q.Cout = h->convs[ci].nb, q.stride = 1;
       q.mode = mode, q.epi.outF = F(p.gxf);
       SDAB_TRY(run_conv(engine, q, st, -1, h->d.in_channels));
-      SDAB_TRY(unpack_f_to_nchw(F(p.gxf), gx, N, h->d.in_channels, h->convs[ci].nb, H, W, st));
+      SDAB_TRY(unpack_f_to_nchw(F(p.gxf), gx, N, wio ? (2 * wio->order + 1) * wio->C : h->d.in_channels,
+                                h->convs[ci].nb, H, W, st));
     }
   }
+  return SDAB_OK;
+}
+
+int check_windows(const sdab_unet* h, const WindowIO& w, int w_end) {
+  SDAB_REQUIRE(w.B >= 1 && w.C >= 1 && w.Cc >= 0 && w.order >= 1 && w.L >= 2 * w.order + 1,
+               "trajectory shorter than the window (MCScoreNet.unfold raises too)");
+  SDAB_REQUIRE(h->d.in_channels == (2 * w.order + 1) * w.C + w.Cc && h->d.out_channels == (2 * w.order + 1) * w.C,
+               "the network's channels do not match (2k+1) C (+ context)");
+  SDAB_REQUIRE(w.w_begin >= 0 && w_end > w.w_begin && w_end <= w.B * (w.L - 2 * w.order), "window range out of bounds");
+  SDAB_REQUIRE(w.cap == 0 || (w.per >= w_end - w.w_begin && w.cap >= w.per), "invalid shard geometry");
   return SDAB_OK;
 }
 
 }  // namespace
 
 extern "C" {
+
+int sdab_unet_forward(sdab_unet* h, const float* x, const float* y, int Nt, int N, int H, int W, float* out,
+                      void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream) {
+  return forward_impl(h, x, y, Nt, N, H, W, out, workspace, workspace_bytes, save, mode, engine, stream, nullptr,
+                      nullptr);
+}
+
+int sdab_mcscore_forward(sdab_unet* h, const float* x, const float* ctx, const float* y, int B, int L, int C, int Cc,
+                         int H, int W, int order, int w_begin, int w_end, float* out, int per, int cap,
+                         void* workspace, size_t workspace_bytes, int save, int mode, int engine, void* stream) {
+  SDAB_REQUIRE(h && (Cc == 0 || ctx), "null argument");
+  const WindowIO w{B, L, C, Cc, order, w_begin, per, cap};
+  SDAB_TRY(check_windows(h, w, w_end));
+  return forward_impl(h, x, y, 1, w_end - w_begin, H, W, out, workspace, workspace_bytes, save, mode, engine, stream, &w,
+                      ctx);
+}
+
+int sdab_mcscore_dgrad(sdab_unet* h, const float* gs, float* gwin, int B, int L, int C, int Cc, int H, int W, int order,
+                       int w_begin, int w_end, void* workspace, size_t workspace_bytes, int mode, int engine,
+                       void* stream) {
+  SDAB_REQUIRE(h != nullptr, "null argument");
+  const WindowIO w{B, L, C, Cc, order, w_begin, 0, 0};
+  SDAB_TRY(check_windows(h, w, w_end));
+  SDAB_REQUIRE(h->sN == w_end - w_begin, "window range differs from the saved forward pass");
+  return backward_impl(h, gs, gwin, workspace, workspace_bytes, mode, engine, stream, nullptr, &w);
+}
 
 int sdab_unet_dgrad(sdab_unet* h, const float* gout, float* gx, void* workspace, size_t workspace_bytes, int mode,
                     int engine, void* stream) {
