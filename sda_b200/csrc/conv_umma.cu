@@ -34,6 +34,9 @@ constexpr int kThreads = 192;
 constexpr int kPatchThreads = 320;  // patch kernel: two epilogue warpgroups (warps 2-5 and 6-9)
 constexpr uint32_t kABytes = 128 * 64;  // one A box: 128 pixels x 32 channels x bf16
 constexpr uint32_t kCtrlBytes = 1024;
+// LayerNorm kernels: bias[512] and shift[512] copies, then the csplit statistics exchange, behind the control block
+constexpr int kCstShift = 512;
+constexpr uint32_t kCstBytes = 4096, kXchgBytes = 4096;
 constexpr uint32_t kStageF = 128 * 128;      // epilogue staging: 128 pixels x 32 fp32 channels (SWIZZLE_128B rows)
 constexpr uint32_t kStageO = 128 * 64;       // 128 pixels x 32 bf16 channels (SWIZZLE_64B rows), one per plane
 constexpr uint32_t kStagingBytes = kStageF + 2 * kStageO;
@@ -506,8 +509,8 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
 template <int LN, bool CTA2>
 __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
                                                  uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
-                                                 uint32_t acc_stride, uint32_t staging_base, float2* xchg,
-                                                 int tile_begin, int tile_end, int warp, int lane, int wg, int nwg,
+                                                 uint32_t acc_stride, uint32_t staging_base, const float* cst,
+                                                 float2* xchg, int tile_begin, int tile_end, int warp, int lane, int wg, int nwg,
                                                  bool csplit) {
   const uint32_t staging0 = staging_base + wg * p.sbufs * kStagingBytes;
   const int issuer = 64 + 128 * wg;
@@ -540,27 +543,28 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
     const bf16* a_pix = (LN == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
     const uint32_t ts = t0 + (uint32_t)C;  // stash columns (adjoint)
-    {
-      // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
-      const int nt = tile + nwg * (int)gridDim.x;
-      if (nt < p.g.num_tiles) {
-        int nn0, nh0, nw0;
-        p.g.tile_origin(nt, nn0, nh0, nw0);
-        const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
-        if (nn < p.N) {
-          const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
-          if (p.epi.res)
-            for (int c = cc0; c < nch; c += ccstep) prefetch_l2(p.epi.res + npix * C + c * 32);
-          if (LN == 2) {
-            const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
-            for (int c = cc0; c < nch; c += ccstep) {
-              prefetch_l2(pa + (size_t)c * bs);
-              prefetch_l2(pa + (size_t)c * bs + lo_off);
-            }
-          }
+    // Pulls the epilogue operands of this thread's pixel of tile `pt` into L2.  Called for the NEXT tile of this
+    // warpgroup between the two sweeps of the current one (and for the very first tile at its start): at the
+    // 5 TB/s these kernels stream, L2 holds some 25 us of traffic, so a request issued a whole tile period
+    // ahead was evicted again before its use (ncu: DRAM reads 2.9 GB above the operand sizes at C = 96).
+    auto prefetch_tile = [&](int pt) {
+      if (pt >= p.g.num_tiles) return;
+      int nn0, nh0, nw0;
+      p.g.tile_origin(pt, nn0, nh0, nw0);
+      const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
+      if (nn >= p.N) return;
+      const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
+      if (p.epi.res)
+        for (int c = cc0; c < nch; c += ccstep) prefetch_l2(p.epi.res + npix * C + c * 32);
+      if (LN == 2) {
+        const bf16* pa = p.epi.ln_a + op_offset(so, nn, nh + 1, nw + 1);
+        for (int c = cc0; c < nch; c += ccstep) {
+          prefetch_l2(pa + (size_t)c * bs);
+          prefetch_l2(pa + (size_t)c * bs + lo_off);
         }
       }
-    }
+    };
+    if (it == wg) prefetch_tile(tile);
 
     // output of one 32-channel block through the staging tiles: F <- v (fp32), then OP <- post(v) (bf16 hi / lo)
     auto stage_and_store = [&](int cc, float (&v)[32], auto&& post) {
@@ -646,8 +650,12 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
     };
 
     if constexpr (LN == 1) {
-      const float* shiftp =
-          p.epi.ln_shift ? p.epi.ln_shift + (size_t)(p.epi.ln_nt > 1 && valid ? n : 0) * p.epi.ln_shift_stride : nullptr;
+      // bias and (one shared) shift vector are read from the copies the kernel made in shared memory: as global
+      // loads they cost an exposed L2 round trip per use (two epilogue warps per scheduler hide nothing)
+      const float* shiftp = !p.epi.ln_shift ? nullptr
+                            : p.epi.ln_nt > 1 ? p.epi.ln_shift + (size_t)(valid ? n : 0) * p.epi.ln_shift_stride
+                                              : cst + kCstShift;
+      const float* biasp = p.epi.bias ? cst : nullptr;
       float rr[32];
       if (has_res) load32(resp + cc0 * 32, rr);
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
@@ -657,10 +665,10 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float f[32];
         tmem_ld32(t0 + cc * 32, f);
-        if (p.epi.bias) {
+        if (biasp) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.epi.bias + cc * 32 + j));
+            const float4 b = *reinterpret_cast<const float4*>(biasp + cc * 32 + j);
             f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
           }
         }
@@ -671,11 +679,11 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           if (cc + ccstep < nch) load32(resp + (cc + ccstep) * 32, rr);
         }
         tmem_st32(t0 + cc * 32, f);
-        if (cc == cc0) K = f[0] + (shiftp ? __ldg(shiftp + cc * 32) : 0.f);
+        if (cc == cc0) K = f[0] + (shiftp ? shiftp[cc * 32] : 0.f);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (shiftp) sh = __ldg(reinterpret_cast<const float4*>(shiftp + cc * 32 + j));
+          if (shiftp) sh = *reinterpret_cast<const float4*>(shiftp + cc * 32 + j);
           const float d0 = f[j] + sh.x - K, d1 = f[j + 1] + sh.y - K, d2 = f[j + 2] + sh.z - K,
                       d3 = f[j + 3] + sh.w - K;
           s1 += d0, s2 += d0 * d0;
@@ -700,6 +708,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       const float rstd = 1.f / sqrtf(m2 * invC1 + 1e-5f);
       if (valid && p.epi.ln_rstd_out && (!csplit || half == 0)) p.epi.ln_rstd_out[pix] = rstd;
       tmem_st_wait();
+      prefetch_tile(tile + nwg * (int)gridDim.x);
       // ---- second sweep: F <- f, OP <- (f + shift - mean) rstd
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float f[32];
@@ -709,7 +718,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (shiftp) sh = __ldg(reinterpret_cast<const float4*>(shiftp + cc * 32 + j));
+            if (shiftp) sh = *reinterpret_cast<const float4*>(shiftp + cc * 32 + j);
             v[j] = (v[j] + sh.x - mean) * rstd, v[j + 1] = (v[j + 1] + sh.y - mean) * rstd;
             v[j + 2] = (v[j + 2] + sh.z - mean) * rstd, v[j + 3] = (v[j + 3] + sh.w - mean) * rstd;
           }
@@ -734,7 +743,8 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           }
         }
         if (stash) tmem_st32(ts + cc * 32, aa);
-        // consumed: request the next block of a, it arrives during the next accumulator load
+        // consumed: request the next block of a, it arrives during the next accumulator load (a second register
+        // buffer was tried: it spills under the 168-register cap of the 320-thread kernel)
         if (valid && cc + ccstep < nch) {
           const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
           load32_hilo(an, an + lo_off, aa);
@@ -749,6 +759,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       }
       const float mg = sg * invC, beta = sga * invC1;
       if (stash) tmem_st_wait();
+      prefetch_tile(tile + nwg * (int)gridDim.x);
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float g[32], a[32];
         if (!stash && valid) {
@@ -844,6 +855,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 160), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  if constexpr (LN != 0) {
+    // bias / shift copies for the LayerNorm epilogue (epilogue_ln_role)
+    float* cst = reinterpret_cast<float*>(base_ptr + kCtrlBytes);
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      cst[i] = p.epi.bias ? p.epi.bias[i] : 0.f;
+      cst[kCstShift + i] = (p.epi.ln_shift && p.epi.ln_nt == 1) ? p.epi.ln_shift[i] : 0.f;
     }
   }
   tc_fence_before();
@@ -968,8 +987,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else {
     // ===================================================================== epilogue (warps 2..5)
     if constexpr (LN != 0)
-      epilogue_ln_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, nullptr,
-                                 tile_begin, tile_end, warp, lane, 0, 1, false);
+      epilogue_ln_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0,
+                                 reinterpret_cast<const float*>(base_ptr + kCtrlBytes), nullptr, tile_begin, tile_end,
+                                 warp, lane, 0, 1, false);
     else
       epilogue_role<CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
                           warp, lane);
@@ -1053,6 +1073,14 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
       asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 352), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  if constexpr (LN != 0) {
+    // bias / shift copies for the LayerNorm epilogue (epilogue_ln_role)
+    float* cst = reinterpret_cast<float*>(base_ptr + kCtrlBytes);
+    for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+      cst[i] = p.epi.bias ? p.epi.bias[i] : 0.f;
+      cst[kCstShift + i] = (p.epi.ln_shift && p.epi.ln_nt == 1) ? p.epi.ln_shift[i] : 0.f;
     }
   }
   tc_fence_before();
@@ -1192,8 +1220,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     if (wg < nwg) {
       if constexpr (LN != 0)
         epilogue_ln_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0,
-                                   reinterpret_cast<float2*>(base_ptr + kCtrlBytes), tile_begin, tile_end, warp, lane,
-                                   wg, nwg, csplit);
+                                   reinterpret_cast<const float*>(base_ptr + kCtrlBytes),
+                                   reinterpret_cast<float2*>(base_ptr + kCtrlBytes + kCstBytes), tile_begin, tile_end,
+                                   warp, lane, wg, nwg, csplit);
       else
         epilogue_role<CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
                             warp, lane, wg, nwg, csplit);
@@ -1297,7 +1326,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(!c.epi.ln || p.staged, "the fused LayerNorm epilogue needs C_out % 32 == 0");
   SDAB_REQUIRE(c.epi.ln != 2 || (c.epi.ln_a && c.epi.ln_rstd_in && !c.epi.bias && !c.epi.act && !c.epi.dact),
                "invalid backward-LayerNorm epilogue");
-  p.ctrl_bytes = kCtrlBytes;
+  p.ctrl_bytes = kCtrlBytes + (c.epi.ln ? kCstBytes : 0);
   p.sbufs = 1;  // measured: deeper store staging does not pay for the ring stages it costs
   if (getenv("SDAB_UMMA_SBUFS")) p.sbufs = atoi(getenv("SDAB_UMMA_SBUFS"));
   SDAB_REQUIRE(p.sbufs >= 1 && p.sbufs <= 3, "staging sets out of range");
@@ -1317,7 +1346,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     p.g.num_tiles = p.g.tiles_w * p.g.tiles_h * p.g.tiles_n;
     p.b_stage_bytes = p.planes * p.b_plane_bytes;
     // csplit statistics exchange of the LayerNorm epilogue: 2 tile parities x 2 warpgroups x 128 pixels x float2
-    if (c.epi.ln && p.acc_stages == 1 && patch_wg == 2) p.ctrl_bytes += 4096;
+    if (c.epi.ln && p.acc_stages == 1 && patch_wg == 2) p.ctrl_bytes += kXchgBytes;
     const uint32_t fixed = p.ctrl_bytes + 1024 + 2 * p.sbufs * kStagingBytes;
     p.a_stages = 3;
     p.stages = (int)((kSmemBudget - fixed - p.a_stages * p.planes * kPatchPlane) / p.b_stage_bytes);

@@ -117,6 +117,25 @@ __global__ void unfold_transpose_kernel(const float* __restrict__ gwin, float* _
   }
 }
 
+// the same sum (same order, so the same bits) four pixels per thread: one (frame, channel) plane per blockIdx.y
+__global__ void unfold_transpose4_kernel(const float4* __restrict__ gwin, float4* __restrict__ gx, int L, int C, int Cc,
+                                         size_t HW4, int order) {
+  const int wdt = 2 * order + 1, nw = L - 2 * order, CH = wdt * C + Cc;
+  const int plane = blockIdx.y, c = plane % C, f = (plane / C) % L, b = plane / (C * L);
+  float4* dst = gx + (size_t)plane * HW4;
+  for (size_t i4 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i4 < HW4; i4 += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < wdt; ++s) {
+      const int i = f - s;
+      if (i >= 0 && i < nw) {
+        const float4 v = gwin[(((size_t)b * nw + i) * CH + s * C + c) * HW4 + i4];
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+    }
+    dst[i4] = acc;
+  }
+}
+
 // score frame (b, f) <- its position in the gathered shards of the window-sharded evaluation (FoldDst, elementwise.cu)
 __global__ void frames_assemble_kernel(const float4* __restrict__ gathered, float4* __restrict__ s, int B, int L, int k,
                                        size_t frame4, int per, int cap) {
@@ -190,6 +209,15 @@ __global__ void predict_kernel(float* __restrict__ x, const float* __restrict__ 
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     x[i] = a * x[i] + b * eps[i];
 }
+// four elements per thread (same arithmetic per element)
+__global__ void predict4_kernel(float4* __restrict__ x, const float4* __restrict__ eps, float a, float b, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = x[i];
+    const float4 e = eps[i];
+    v.x = a * v.x + b * e.x, v.y = a * v.y + b * e.y, v.z = a * v.z + b * e.z, v.w = a * v.w + b * e.w;
+    x[i] = v;
+  }
+}
 
 // partial[b][p] = sum over the p-th slice of eps_b^2 (fixed slicing -> deterministic)
 __global__ void sumsq_partial_kernel(const float* __restrict__ eps, float* __restrict__ partial, size_t event) {
@@ -244,6 +272,14 @@ __global__ void tweedie_kernel(const float* __restrict__ x, const float* __restr
                                float* __restrict__ xhat, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     xhat[i] = (x[i] - sigma * eps[i]) / mu;
+}
+__global__ void tweedie4_kernel(const float4* __restrict__ x, const float4* __restrict__ eps, float mu, float sigma,
+                                float4* __restrict__ xhat, size_t n4) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = x[i], e = eps[i];
+    xhat[i] = make_float4((v.x - sigma * e.x) / mu, (v.y - sigma * e.y) / mu, (v.z - sigma * e.z) / mu,
+                          (v.w - sigma * e.w) / mu);
+  }
 }
 
 __global__ void axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
@@ -328,9 +364,16 @@ int sdab_unfold_transpose_add(const float* gwin, float* gx, int B, int L, int C,
   SDAB_REQUIRE(gwin && gx, "null argument");
   SDAB_REQUIRE(order >= 1 && L >= 2 * order + 1, "trajectory shorter than the window");
   SDAB_TRY(sdab_device_check());
-  const size_t total = (size_t)B * L * C * H * W;
-  unfold_transpose_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)stream>>>(gwin, gx, B, L, C, Cc, (size_t)H * W,
-                                                                               order);
+  const size_t HW = (size_t)H * W;
+  if (HW % 4 == 0 && (size_t)B * L * C <= 65535) {
+    const size_t HW4 = HW / 4;
+    const int gx4 = (int)((HW4 + kBlock - 1) / kBlock < 64 ? (HW4 + kBlock - 1) / kBlock : 64);
+    unfold_transpose4_kernel<<<dim3(gx4, B * L * C), kBlock, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(gwin), reinterpret_cast<float4*>(gx), L, C, Cc, HW4, order);
+  } else {
+    const size_t total = (size_t)B * L * C * HW;
+    unfold_transpose_kernel<<<grid_for(total), kBlock, 0, (cudaStream_t)stream>>>(gwin, gx, B, L, C, Cc, HW, order);
+  }
   SDAB_LAUNCH_CHECK("unfold_transpose_kernel");
   return SDAB_OK;
 }
@@ -352,7 +395,11 @@ int sdab_frames_assemble(const float* gathered, float* s, int B, int L, int C, i
 int sdab_vpsde_predict(float* x, const float* eps, float a, float b, size_t n, void* stream) {
   SDAB_REQUIRE(x && eps, "null argument");
   SDAB_TRY(sdab_device_check());
-  predict_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, eps, a, b, n);
+  if (n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)eps & 15) == 0)
+    predict4_kernel<<<grid_for(n / 4), kBlock, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(x),
+                                                                         reinterpret_cast<const float4*>(eps), a, b, n / 4);
+  else
+    predict_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, eps, a, b, n);
   SDAB_LAUNCH_CHECK("predict_kernel");
   return SDAB_OK;
 }
@@ -384,7 +431,12 @@ int sdab_randn(float* out, size_t n, uint64_t seed, uint64_t offset, void* strea
 int sdab_tweedie(const float* x, const float* eps, float mu, float sigma, float* xhat, size_t n, void* stream) {
   SDAB_REQUIRE(x && eps && xhat, "null argument");
   SDAB_TRY(sdab_device_check());
-  tweedie_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, eps, mu, sigma, xhat, n);
+  if (n % 4 == 0 && (((uintptr_t)x | (uintptr_t)eps | (uintptr_t)xhat) & 15) == 0)
+    tweedie4_kernel<<<grid_for(n / 4), kBlock, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(eps), mu, sigma,
+        reinterpret_cast<float4*>(xhat), n / 4);
+  else
+    tweedie_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, eps, mu, sigma, xhat, n);
   SDAB_LAUNCH_CHECK("tweedie_kernel");
   return SDAB_OK;
 }

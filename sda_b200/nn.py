@@ -302,6 +302,7 @@ class UNet(nn.Module):
         self._workspace = None
         self._forward_token = 0
         self._saved_level = 0
+        self._buffers_mc = {}  # persistent gather buffers of the window-sharded evaluation
 
     # ------------------------------------------------------------------ reference module-tree forward
     def _module_forward(self, x: Tensor, y: Tensor) -> Tensor:
@@ -355,6 +356,8 @@ class UNet(nn.Module):
 
         for k in ('_handle', '_packed', '_packed_key', '_workspace'):
             state[k] = None
+
+        state['_buffers_mc'] = {}
 
         return state
 
@@ -527,6 +530,50 @@ class UNet(nn.Module):
             )
 
         return gx, [t for pair in zip(dws, dbs) for t in pair], dshift
+
+    # ------------------------------------------------------------------ trajectory-level entry (MCScoreNet)
+    def _native_mcscore_forward(self, x: Tensor, y: Tensor, ctx, order: int, begin: int, end: int, out: Tensor,
+                                per: int, cap: int, save: int) -> None:
+        r"""sdab_mcscore_forward: the windows [begin, end) of trajectory `x` (B, L, C, H, W) through the network
+        with unfold / context concat / fold as addressing; frames are written into `out` (include/sdab.h)."""
+
+        with torch.cuda.device(x.device):
+            lib = self._ensure_handle(x.device)
+            B, L, C, H, W = x.shape
+            Cc = 0 if ctx is None else ctx.shape[0]
+            y = y.detach().to(torch.float32).reshape(-1, y.shape[-1]).contiguous()
+
+            if y.shape[0] != 1:
+                raise RuntimeError('the fused window path takes one diffusion time per call')
+
+            ws = self._get_workspace(lib, end - begin, H, W, save, x.device)
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            self._forward_token += 1
+            self._saved_mode = (_mode(), _engine())
+            self._saved_level = int(save)
+            _lib.check(
+                lib.sdab_mcscore_forward(
+                    self._handle, x.data_ptr(), None if ctx is None else ctx.data_ptr(), y.data_ptr(), B, L, C, Cc, H, W,
+                    order, begin, end, out.data_ptr(), per, cap, base, ws.numel() - (base - ws.data_ptr()), int(save),
+                    self._saved_mode[0], self._saved_mode[1], _lib.stream_ptr(),
+                )
+            )
+
+    def _native_mcscore_dgrad(self, g: Tensor, gwin: Tensor, Cc: int, order: int, begin: int, end: int) -> None:
+        r"""sdab_mcscore_dgrad: cotangent of the folded score (B, L, C, H, W) -> window input-gradients of the
+        windows [begin, end), written at gwin[begin:end] ((2k+1) C channels each)."""
+
+        with torch.cuda.device(g.device):
+            lib = _lib.load()
+            B, L, C, H, W = g.shape
+            ws = self._workspace
+            base = (ws.data_ptr() + 1023) // 1024 * 1024
+            _lib.check(
+                lib.sdab_mcscore_dgrad(
+                    self._handle, g.data_ptr(), gwin[begin:].data_ptr(), B, L, C, Cc, H, W, order, begin, end, base,
+                    ws.numel() - (base - ws.data_ptr()), self._saved_mode[0], self._saved_mode[1], _lib.stream_ptr(),
+                )
+            )
 
     def forward(self, x: Tensor, y: Tensor) -> Tensor:
         if not self._native:

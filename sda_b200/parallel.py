@@ -5,17 +5,24 @@ scaling is algorithmic: the score of a trajectory is composed from independent w
 scores (sda/score.py:134-144).  That independence is the data-parallel axis used here:
 
 * one process per GPU (torchrun), every rank holds the full trajectory `x`, advances
-  it with the same counter-based Philox noise, and therefore stays bit-identical;
-* per score evaluation each rank runs the U-Net on a contiguous range of the
-  flattened (B, L - 2k) windows, then ONE all-gather (NCCL over NVLink / NVSwitch)
-  rebuilds the full window-score tensor;
+  it with the same counter-based Philox noise, and therefore stays bit-identical
+  (`VPSDE.sample` / `sampler_state` broadcast the initial noise and the seed from the
+  first rank of the group);
+* per score evaluation each rank runs the U-Net on a contiguous range of the flattened
+  (B, L - 2k) windows -- it reads its windows straight from the trajectory and writes
+  only the frames they feed (`fold` keeps one of the 2k + 1 slots of an interior
+  window) into its shard of ONE in-place all-gather (NCCL over NVLink / NVSwitch):
+  32 MiB in total at 256 x 256, L = 64, instead of the 157 MB of window scores;
 * when the evaluation is differentiated (GaussianScore), the backward pass runs the
-  input-VJP of the local windows only and all-gathers the window input-gradients;
-  the overlap-add that follows (`unfold` adjoint) is local and in fixed order, so
-  the result does not depend on the number of ranks.
+  input-VJP of the local windows only and all-gathers the window input-gradients in
+  place; the overlap-add that follows (`unfold` adjoint) is local and in fixed order,
+  so the result does not depend on the number of ranks.
 
 `shard_windows(score)` switches a `MCScoreNet` to this mode; nothing else changes for
-the caller.
+the caller.  Evaluations the fused window path does not serve (CPU tensors, per-sample
+times, a kernel that is not a native `ScoreUNet`, parameter gradients) fall back to
+`_ShardedKernel`: the windows are materialised, the local range goes through the kernel
+and the window scores / window input-gradients are all-gathered.
 """
 
 from __future__ import annotations
@@ -26,7 +33,7 @@ import torch
 import torch.distributed as dist
 from torch import Tensor
 
-from .score import MCScoreNet
+from .score import MCScoreNet, shard_geometry
 
 
 def window_range(n_windows: int, rank: int, world: int):
@@ -94,13 +101,17 @@ def _gather(local: Tensor, per: int, total: int, group) -> Tensor:
 
 
 class ShardedMCScoreNet(MCScoreNet):
-    r"""`MCScoreNet` whose kernel evaluations are sharded over `group` (see module docstring)."""
+    r"""`MCScoreNet` whose kernel evaluations are sharded over `shard_group` (see module docstring)."""
 
+    _sdab_sharded = True
     shard_group = None
 
     def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.shard_group) == 1 or t.dim() > 0:
             return super().forward(x, t, c)
+
+        if self._fusable(x, t):
+            return super().forward(x, t, c)  # fused window path; the shard group travels in the WindowBatch
 
         xw = self.unfold(x, self.order)
         s = _ShardedKernel.apply(xw, self.kernel, t, c, self.shard_group)
@@ -118,3 +129,6 @@ def shard_windows(score: MCScoreNet, group=None) -> MCScoreNet:
     score.shard_group = group
 
     return score
+
+
+__all__ = ['shard_windows', 'ShardedMCScoreNet', 'window_range', 'shard_geometry']

@@ -31,6 +31,7 @@ from torch import Size, Tensor
 from . import _lib
 from .nn import *  # noqa: F401,F403  (the reference re-exports sda.nn from sda.score)
 from .nn import ResMLP, UNet, input_gradient_only
+from . import nn as _nn
 
 try:  # progress bar as in the reference (sda/score.py:250); optional here
     from tqdm import tqdm
@@ -96,6 +97,9 @@ class ScoreUNet(nn.Module):
         self.network = UNet(channels + context, channels, embedding, **kwargs)
 
     def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        if isinstance(x, WindowBatch):
+            return _score_windows(self, x, t, c)
+
         dims = self.network.spatial + 1
 
         if c is None:
@@ -183,6 +187,146 @@ class _Fold(torch.autograd.Function):
         return gs, None
 
 
+class WindowBatch:
+    r"""Stand-in for the unfolded window tensor (B, L - 2k, (2k+1) C, H, W) that `MCScoreNet.forward` hands to
+    a `ScoreUNet` kernel on the native path: it carries the TRAJECTORY, and the network reads its windows (and
+    writes the folded score) by addressing (sdab_mcscore_forward) instead of through materialised unfold / cat /
+    fold tensors.  A `ScoreUNet` subclass that only forwards `x` to `super().forward` (as the reference's
+    LocalScoreUNet does, experiments/kolmogorov/utils.py:45-46) works unchanged; one that computes on `x` should
+    call `x.materialize()` first, or set `MCScoreNet.fuse_windows = False`."""
+
+    def __init__(self, x: Tensor, order: int, group=None):
+        self.x, self.order, self.group = x, order, group
+
+    @property
+    def shape(self):
+        B, L, C, H, W = self.x.shape
+        return torch.Size((B, L - 2 * self.order, (2 * self.order + 1) * C, H, W))
+
+    def materialize(self) -> Tensor:
+        return MCScoreNet.unfold(self.x, self.order)
+
+
+def shard_geometry(n_windows: int, windows_per_trajectory: int, order: int, rank: int, world: int):
+    r"""Window range [begin, end) of `rank`, windows per rank `per` and frames per shard `cap` of the
+    window-sharded evaluation (include/sdab.h: sdab_mcscore_forward)."""
+
+    per = -(-n_windows // world)
+    begin = min(rank * per, n_windows)
+    end = min(begin + per, n_windows)
+    touched = (per + windows_per_trajectory - 2) // windows_per_trajectory + 1
+
+    return begin, end, per, per + 2 * order * touched
+
+
+class _MCScore(torch.autograd.Function):
+    r"""MCScoreNet.forward (sda/score.py:134-144) as one library call per rank: unfold, the context concat and
+    fold are addressing inside the network's first and last layer.  Window-sharded (group of > 1 ranks): every
+    rank evaluates a contiguous range of the flattened windows and ONE all-gather (NCCL over NVLink) moves the
+    frames each range feeds (32 MiB at 256 x 256, L = 64, whatever the number of ranks); the backward all-gathers
+    the window input-gradients and overlap-adds them locally in fixed order, so the result is bit-identical for
+    any number of ranks.  Differentiable w.r.t. the trajectory only."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, y: Tensor, cvals, net: UNet, order: int, group) -> Tensor:
+        import torch.distributed as dist
+
+        B, L, C, H, W = x.shape
+        nw = L - 2 * order
+        sharded = group is not False
+        world = dist.get_world_size(group) if sharded else 1
+        rank = dist.get_rank(group) if sharded else 0
+        begin, end, per, cap = shard_geometry(B * nw, nw, order, rank, world)
+        save = int(getattr(_nn._scope, 'grad_enabled', True) and ctx.needs_input_grad[0])
+        x = x.detach().contiguous()
+        out = torch.empty_like(x)
+        lib = _lib.load()
+
+        if world == 1:
+            net._native_mcscore_forward(x, y, cvals, order, 0, B * nw, out, 0, 0, save)
+        else:
+            key = ('fwd', world, cap, C, H, W, x.device)
+            buf = net._buffers_mc.get(key)
+
+            if buf is None:
+                buf = net._buffers_mc[key] = torch.empty((world * cap, C, H, W), dtype=torch.float32, device=x.device)
+
+            if end > begin:
+                net._native_mcscore_forward(x, y, cvals, order, begin, end, buf[rank * cap:], per, cap, save)
+
+            dist.all_gather_into_tensor(buf, buf[rank * cap:(rank + 1) * cap], group=group)
+
+            with torch.cuda.device(x.device):
+                _lib.check(lib.sdab_frames_assemble(buf.data_ptr(), out.data_ptr(), B, L, C, H, W, order, per, cap, _lib.stream_ptr()))
+
+        ctx.net, ctx.save, ctx.token = net, save, net._forward_token
+        ctx.meta = (order, group, world, rank, begin, end, per, 0 if cvals is None else cvals.shape[0])
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        import torch.distributed as dist
+
+        net = ctx.net
+        order, group, world, rank, begin, end, per, Cc = ctx.meta
+
+        if not ctx.save:
+            return (None,) * 6
+
+        if ctx.token != net._forward_token:
+            raise RuntimeError(
+                'sda_b200.score.MCScoreNet: backward through a forward pass whose saved activations were '
+                'overwritten by a later forward of the same network'
+            )
+
+        g = g.detach().to(torch.float32).contiguous()
+        B, L, C, H, W = g.shape
+        key = ('bwd', world, per, C, H, W, g.device)
+        gwin = net._buffers_mc.get(key)
+
+        if gwin is None:
+            gwin = net._buffers_mc[key] = torch.empty((world * per, (2 * order + 1) * C, H, W), dtype=torch.float32, device=g.device)
+
+        if end > begin:
+            net._native_mcscore_dgrad(g, gwin, Cc, order, begin, end)
+
+        if world > 1:
+            dist.all_gather_into_tensor(gwin, gwin[rank * per:(rank + 1) * per], group=group)
+
+        gx = torch.empty_like(g)
+
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.load().sdab_unfold_transpose_add(gwin.data_ptr(), gx.data_ptr(), B, L, C, 0, H, W, order, _lib.stream_ptr()))
+
+        return gx, None, None, None, None, None
+
+
+def _score_windows(kernel: 'ScoreUNet', wb: WindowBatch, t: Tensor, c) -> Tensor:
+    r"""ScoreUNet.forward on a WindowBatch: returns the FOLDED score (B, L, C, H, W)."""
+
+    x = wb.x
+    H, W = x.shape[-2:]
+
+    if c is not None:
+        # the context must be one stack of planes shared by every window (the forcing channel of
+        # LocalScoreUNet); anything else goes through the materialised windows
+        if c.dim() < 2 or tuple(c.shape[-2:]) != (H, W) or c.numel() != c.shape[-3 if c.dim() > 2 else -2] * H * W or c.requires_grad:
+            xw = wb.materialize()
+            return MCScoreNet.fold(ScoreUNet.forward(kernel, xw, t, c), wb.order)
+
+        c = c.detach().to(torch.float32).reshape(-1, H, W).contiguous()
+
+    y = kernel.embedding(t.reshape(-1))
+    prev = getattr(_nn._scope, 'grad_enabled', True)
+    _nn._scope.grad_enabled = torch.is_grad_enabled()
+
+    try:
+        return _MCScore.apply(x, y, c, kernel.network, wb.order, wb.group)
+    finally:
+        _nn._scope.grad_enabled = prev
+
+
 class MCScoreNet(nn.Module):
     r"""Score of a Markov chain composed from window scores.  Reference: sda/score.py:113-164.
 
@@ -202,12 +346,47 @@ class MCScoreNet(nn.Module):
 
         self.kernel = build(features * (2 * order + 1), context, **kwargs)
 
+    fuse_windows = True  # native path: unfold / context concat / fold as addressing inside the network
+    shard_group = False  # False: not sharded; None / a process group: window-sharded (sda_b200.parallel)
+    _sdab_sharded = False
+
     def forward(self, x: Tensor, t: Tensor, c: Tensor = None) -> Tensor:
+        if self._fusable(x, t):
+            return self.kernel(WindowBatch(x, self.order, self._group()), t, c)
+
         x = self.unfold(x, self.order)
         s = self.kernel(x, t, c)
         s = self.fold(s, self.order)
 
         return s
+
+    def _group(self):
+        import torch.distributed as dist
+
+        if self._sdab_sharded and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.shard_group) > 1:
+            return self.shard_group
+
+        return False
+
+    def _fusable(self, x: Tensor, t: Tensor) -> bool:
+        r"""The fused window path serves evaluations that are differentiated w.r.t. the trajectory at most
+        (sampling, likelihood guidance): CUDA fp32 trajectory, one diffusion time, native U-Net kernel."""
+
+        if not (self.fuse_windows and self.order >= 1 and _is_native(x) and isinstance(self.kernel, ScoreUNet)):
+            return False
+
+        net = self.kernel.network
+
+        if not (isinstance(net, UNet) and net._native and t.dim() == 0 and not t.requires_grad):
+            return False
+
+        if x.shape[1] < 2 * self.order + 1 or (2 * self.order + 1) * x.shape[2] != net.out_channels:
+            return False
+
+        if torch.is_grad_enabled() and not getattr(_nn._scope, 'input_only', False):
+            return not any(p.requires_grad for p in self.kernel.parameters())
+
+        return True
 
     @staticmethod
     def unfold(x: Tensor, order: int) -> Tensor:

@@ -27,23 +27,41 @@ def _worker(rank, world, port, results):
         from oracle.testing import randn
         from sda_b200.parallel import shard_windows
 
-        score, k = build_score('net_small', 32, 'cuda')
-        x = randn((1, 9, 2, 32, 32), seed=1).cuda()   # 7 windows: uneven 4 / 3 split
-        y = randn((1, 9, 2, 16, 16), seed=2).cuda()
-        t = torch.tensor(0.45).cuda()
-        A = lambda v: v[..., ::2, ::2]  # noqa: E731
+        ok = True
 
-        def guided(s):
-            return sc.GaussianScore(y, A=A, std=0.1, sde=sc.VPSDE(s, shape=()), gamma=1e-2).cuda()(x, t)
+        for B, L in ((1, 9), (2, 6)):   # 7 windows: uneven 4 / 3 split; 2 x 4 windows: one trajectory per rank
+            score, k = build_score('net_small', 32, 'cuda')
+            x = randn((B, L, 2, 32, 32), seed=1).cuda()
+            y = randn((B, L, 2, 16, 16), seed=2).cuda()
+            t = torch.tensor(0.45).cuda()
+            A = lambda v: v[..., ::2, ::2]  # noqa: E731
 
-        with torch.no_grad():
-            plain = score(x, t)
-        plain_g = guided(score)
-        shard_windows(score)
-        with torch.no_grad():
-            sharded = score(x, t)
-        sharded_g = guided(score)
-        results[rank] = bool(torch.equal(plain, sharded) and torch.equal(plain_g, sharded_g))
+            def guided(s):
+                return sc.GaussianScore(y, A=A, std=0.1, sde=sc.VPSDE(s, shape=()), gamma=1e-2).cuda()(x, t)
+
+            with torch.no_grad():
+                plain = score(x, t)
+            plain_g = guided(score)
+            shard_windows(score)
+            with torch.no_grad():
+                sharded = score(x, t)
+            sharded_g = guided(score)
+            ok = ok and bool(torch.equal(plain, sharded) and torch.equal(plain_g, sharded_g))
+            # the materialised fallback of the sharded path (per-window kernels that are not fusable)
+            score.fuse_windows = False
+            with torch.no_grad():
+                ok = ok and bool(torch.equal(plain, score(x, t)))
+            ok = ok and bool(torch.equal(plain_g, guided(score)))
+            score.fuse_windows = True
+
+        # ranks seeded differently still sample the same trajectory: rank 0's noise and Philox seed are broadcast
+        torch.manual_seed(100 + rank)
+        sde = sc.VPSDE(sc.GaussianScore(y, A=A, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2), shape=(L, 2, 32, 32)).cuda()
+        sample = sde.sample((B,), steps=2, corrections=1, tau=0.5)
+        both = [torch.empty_like(sample) for _ in range(world)]
+        dist.all_gather(both, sample)
+        ok = ok and bool(torch.isfinite(sample).all()) and all(bool(torch.equal(both[0], o)) for o in both)
+        results[rank] = ok
     finally:
         dist.destroy_process_group()
 

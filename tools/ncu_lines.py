@@ -40,10 +40,19 @@ base = min(a for a, _, _ in recs)
 # pick the function section of the disassembly matching the profiled kernel (template args in the mangled name)
 sections = re.split(r'\n(?=\s*\.section\s+\.text\.)', dis)
 want = None
-m = re.search(r'conv_umma_kernel<(?:\(int\))?(\d+), (?:\(int\))?(\d+)>', name)
+m = re.search(r'(\w+)<([^>]*)>', name)
+mangled = None
+if m:
+    parts = []
+    for a in m.group(2).split(','):
+        a = a.strip()
+        mm = re.match(r'\((\w+)\)(\d+)', a)
+        ty, val = (mm.group(1), mm.group(2)) if mm else ('int', a)
+        parts.append(('Lb' if ty == 'bool' else 'Li') + val + 'E')
+    mangled = m.group(1) + 'I' + ''.join(parts) + 'E'
 for sec in sections:
-    head = sec[:400]
-    if kern in head and (m is None or f'ILi{m.group(1)}ELi{m.group(2)}E' in head):
+    head = sec[:600]
+    if (mangled and mangled in head) or (mangled is None and kern in head):
         want = sec
         break
 if want is None:
