@@ -75,8 +75,10 @@ def _face_value(c, u_face, axis, dt, h):
     return upwind - (upwind - high) * phi
 
 
-def explicit_terms(u, v, dt, h, nu, forcing_u):
-    r"""convection + diffusion + forcing of navier_stokes_explicit_terms, for both components."""
+def explicit_terms(u, v, dt, h, nu, forcing_u, drag=0.1):
+    r"""convection + diffusion + forcing of navier_stokes_explicit_terms, for both components.
+    `forcing_u` = 0 and `drag` = 0 switch the Kolmogorov forcing off (unforced Navier-Stokes: the analytic
+    anchors of tests/test_oracle.py); the reference always runs with both on (mcs.py:266-272)."""
 
     ax, ay = -2, -1
     out = []
@@ -93,7 +95,7 @@ def explicit_terms(u, v, dt, h, nu, forcing_u):
         fy = _face_value(c, vy, ay, dt, h) * vy
         conv = -((fx - _shift(fx, -1, ax)) + (fy - _shift(fy, -1, ay))) / h
         lap = (_shift(c, 1, ax) + _shift(c, -1, ax) + _shift(c, 1, ay) + _shift(c, -1, ay) - 4 * c) / h ** 2
-        force = (forcing_u if comp == 0 else 0) - 0.1 * c
+        force = (forcing_u if comp == 0 else 0) - drag * c
         out.append(conv + nu * lap + force)
 
     return out
@@ -129,19 +131,21 @@ def forcing_profile(size: int, dtype):
     return np.sin(4 * y).astype(dtype)[None, :]
 
 
-def transition(x: np.ndarray, dt: float = 0.2, reynolds: float = 1e3, n_inner: int | None = None) -> np.ndarray:
-    r"""KolmogorovFlow.transition (mcs.py:333-338, inner function :307-316). x: (..., 2, N, N)."""
+def transition(x: np.ndarray, dt: float = 0.2, reynolds: float = 1e3, n_inner: int | None = None, forced: bool = True) -> np.ndarray:
+    r"""KolmogorovFlow.transition (mcs.py:333-338, inner function :307-316). x: (..., 2, N, N).
+    forced=False: no Kolmogorov forcing and no linear drag (test anchors only)."""
 
     size = x.shape[-1]
     h = x.dtype.type(2 * math.pi / size)
     steps = inner_steps(size, dt)
     sub = x.dtype.type(dt / steps)
     nu = x.dtype.type(1 / reynolds)
-    f = forcing_profile(size, x.dtype)
+    f = forcing_profile(size, x.dtype) if forced else x.dtype.type(0)
+    drag = x.dtype.type(0.1 if forced else 0.0)
     u, v = x[..., 0, :, :], x[..., 1, :, :]
 
     for _ in range(steps if n_inner is None else n_inner):
-        du, dv = explicit_terms(u, v, sub, h, nu, f)
+        du, dv = explicit_terms(u, v, sub, h, nu, f, drag)
         u, v = project(u + sub * du, v + sub * dv, h)
 
     return np.stack((u, v), axis=-3).astype(x.dtype)

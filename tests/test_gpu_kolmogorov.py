@@ -116,3 +116,23 @@ def test_generate_then_train_pipeline(tmp_path):
     sde = sc.VPSDE(kernel, shape=(6, 16, 16)).cuda()
     losses = [lt for lt, lv, lr in loop(sde, train, valid, epochs=6, batch_size=4, learning_rate=2e-3, device='cuda')]
     assert all(np.isfinite(losses)) and min(losses[3:]) < losses[0]
+
+
+@pytest.mark.parametrize('size', [32, 64])
+def test_kernels_reach_the_laminar_kolmogorov_flow(size):
+    r"""An anchor that does not go through the (unpinned) oracle: at Re = 10 the forced flow converges to the
+    exact steady state u = A sin(4 y), v = 0, A = 1 / (nu |lambda_4| + 0.1) (tests/test_oracle.py).  size = 64
+    runs the fused fast path, 32 the generic kernels."""
+
+    import math
+
+    from sda_b200.mcs import KolmogorovFlow
+
+    nu = 0.1
+    chain = KolmogorovFlow(size=size, dt=0.2, reynolds=1 / nu)
+    x = chain.trajectory(torch.zeros(2, 2, size, size), 60, last=True).cpu().numpy().astype(np.float64)
+    h = 2 * math.pi / size
+    amp = 1 / (nu * (2 - 2 * math.cos(4 * h)) / h ** 2 + 0.1)
+    exact = amp * np.sin(4 * (np.arange(size) + 0.5) * h)[None, :] * np.ones((size, 1))
+    assert np.abs(x[:, 0] - exact).max() < 2e-5 * amp
+    assert np.abs(x[:, 1]).max() < 2e-5 * amp

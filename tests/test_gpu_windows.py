@@ -47,9 +47,10 @@ def test_fused_path_is_taken_and_falls_back():
     score, k = build_score('net_small', 16, 'cuda')
     x = randn((1, 6, 2, 16, 16), seed=3).cuda()
     t = torch.tensor(0.3).cuda()
-    assert score._fusable(x, t)
-    assert not score._fusable(x, torch.tensor([0.3]).cuda())  # per-trajectory times: materialised path
-    assert not score._fusable(x.cpu(), t.cpu())
+    with torch.no_grad():
+        assert score._fusable(x, t)
+        assert not score._fusable(x, torch.tensor([0.3]).cuda())  # per-trajectory times: materialised path
+        assert not score._fusable(x.cpu(), t.cpu())
 
     with torch.enable_grad():  # trainable parameters and grad mode on: the training path keeps autograd's route
         assert not score._fusable(x, t)

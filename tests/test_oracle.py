@@ -101,3 +101,66 @@ def test_kolmogorov_oracle_invariants():
     assert np.sqrt((y ** 2).sum(-3)).max() < 5.0
     y32 = ko.transition(x.astype(np.float32), dt=0.2)
     assert np.linalg.norm(y32 - y) / np.linalg.norm(y) < 1e-5
+
+
+# --------------------------------------------------------------------------- stepper oracle: analytic anchors
+# jax-cfd is absent (parity unpinned by the reference, oracle/kolmogorov_oracle.py header), so the restated
+# scheme is anchored on exact solutions of the incompressible Navier-Stokes equations instead of on memory.
+def _taylor_green(N, amp=1.0):
+    r"""u = sin x cos y, v = -cos x sin y on the staggered MAC positions (u at ((i+1)h, (j+1/2)h), v at
+    ((i+1/2)h, (j+1)h)): an exact solution of unforced Navier-Stokes decaying as exp(-2 nu t)."""
+
+    import math
+
+    h = 2 * math.pi / N
+    xu, yu = (np.arange(N) + 1) * h, (np.arange(N) + 0.5) * h
+    xv, yv = (np.arange(N) + 0.5) * h, (np.arange(N) + 1) * h
+
+    return amp * np.stack((np.sin(xu)[:, None] * np.cos(yu)[None, :], -np.cos(xv)[:, None] * np.sin(yv)[None, :]))
+
+
+def test_stepper_oracle_reproduces_taylor_green_decay_at_second_order():
+    import math
+
+    from oracle import kolmogorov_oracle as ko
+
+    nu, T, errs = 1e-2, 1.0, {}
+
+    for N in (16, 32, 64):
+        h = 2 * math.pi / N
+        n = int(round(T / (0.2 * h * h)))  # dt ~ h^2: the forward-Euler error stays below the spatial one
+        x = _taylor_green(N)
+
+        for _ in range(n):
+            x = ko.transition(x, dt=T / n, reynolds=1 / nu, forced=False)
+
+        exact = _taylor_green(N, math.exp(-2 * nu * T))
+        errs[N] = np.linalg.norm(x - exact) / np.linalg.norm(exact)
+        assert np.abs(ko.divergence(x)).max() < 1e-12
+
+    assert errs[64] < 1e-3
+    # second-order convergence in h (van Leer limited Lax-Wendroff advection, centred diffusion and projection)
+    assert errs[16] / errs[32] > 3.5 and errs[32] / errs[64] > 3.5
+
+
+def test_stepper_oracle_reaches_the_laminar_kolmogorov_flow():
+    r"""Forced, at Re = 10 (linearly stable): the steady state is u = A sin(4 y), v = 0 with
+    A = 1 / (nu |lambda_4| + 0.1), lambda_4 the discrete Laplacian eigenvalue of sin(4 y).  Pins the forcing
+    amplitude (1), wavenumber (4), offset (u sits at y_{j+1/2}), the drag (-0.1 u) and the viscosity."""
+
+    import math
+
+    from oracle import kolmogorov_oracle as ko
+
+    N, nu = 32, 0.1
+    h = 2 * math.pi / N
+    x = np.zeros((2, N, N))
+
+    for _ in range(60):
+        x = ko.transition(x, dt=0.2, reynolds=1 / nu)
+
+    amp = 1 / (nu * (2 - 2 * math.cos(4 * h)) / h ** 2 + 0.1)
+    exact = amp * np.sin(4 * (np.arange(N) + 0.5) * h)[None, :] * np.ones((N, 1))
+    assert np.abs(x[0] - exact).max() < 1e-7 * amp
+    assert np.abs(x[1]).max() < 1e-12
+    assert abs(amp - 1 / (16 * nu + 0.1)) < 0.05  # the continuum value, for orientation
