@@ -228,6 +228,16 @@ int sdab_kolmogorov_prior(sdab_kolmogorov* h, float* uv, int E, uint64_t seed, v
 /* observation helpers (mcs.py:340-347, :361-375) */
 int sdab_coarsen(const float* x, float* out, size_t n_img, int H, int W, int r, void* stream);
 int sdab_vorticity(const float* x, float* out, size_t n_pair, int H, int W, void* stream);
+/* Adjoints (vector-Jacobian products) of the two operators above, and KolmogorovFlow.upsample(mode='bilinear')
+ * (mcs.py:349-359: circular pad 1 -> F.interpolate(scale_factor=r) -> crop r) with its adjoint: the observation
+ * operators A(x) of the guided sampler are differentiated at every score evaluation (score.py:389-394).
+ *   coarsen_adjoint : g (n_img, H/r, W/r) -> gx (n_img, H, W)
+ *   vorticity_adjoint: g (n_pair, H, W)   -> gx (n_pair, 2, H, W)
+ *   upsample        : x (n_img, H, W)     -> out (n_img, r H, r W);  adjoint: g (n_img, r H, r W) -> gx (n_img, H, W) */
+int sdab_coarsen_adjoint(const float* g, float* gx, size_t n_img, int H, int W, int r, void* stream);
+int sdab_vorticity_adjoint(const float* g, float* gx, size_t n_pair, int H, int W, void* stream);
+int sdab_upsample_bilinear(const float* x, float* out, size_t n_img, int H, int W, int r, void* stream);
+int sdab_upsample_bilinear_adjoint(const float* g, float* gx, size_t n_img, int H, int W, int r, void* stream);
 
 #ifdef __cplusplus
 }

@@ -86,6 +86,10 @@ _PROTOTYPES = {
     'sdab_kolmogorov_prior': (c_int, [c_void_p, c_void_p, c_int, c_uint64, c_void_p, c_size_t, c_void_p]),
     'sdab_coarsen': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
     'sdab_vorticity': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    'sdab_coarsen_adjoint': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    'sdab_vorticity_adjoint': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p]),
+    'sdab_upsample_bilinear': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
+    'sdab_upsample_bilinear_adjoint': (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_int, c_void_p]),
 }
 
 SYMBOLS = tuple(_PROTOTYPES)

@@ -320,6 +320,95 @@ __global__ void vorticity_kernel(const float* __restrict__ x, float* __restrict_
   }
 }
 
+// adjoint of coarsen: gx[h, w] = g[h / r, w / r] / r^2
+__global__ void coarsen_adjoint_kernel(const float* __restrict__ g, float* __restrict__ gx, size_t n_img, int H, int W,
+                                       int r) {
+  const int Ho = H / r, Wo = W / r;
+  const size_t total = n_img * H * W;
+  const float inv = 1.f / (float)(r * r);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = idx % W, h = (idx / W) % H;
+    const size_t img = idx / ((size_t)W * H);
+    gx[idx] = g[(img * Ho + h / r) * Wo + w / r] * inv;
+  }
+}
+
+// adjoint of vorticity: gu[h, w] = (g[h, w-1] - g[h, w+1]) / 2, gv[h, w] = (g[h+1, w] - g[h-1, w]) / 2 (circular)
+__global__ void vorticity_adjoint_kernel(const float* __restrict__ g, float* __restrict__ gx, size_t n_pair, int H,
+                                         int W) {
+  const size_t total = n_pair * H * W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = idx % W, h = (idx / W) % H;
+    const size_t pair = idx / ((size_t)W * H);
+    const float* gp = g + pair * H * W;
+    const int wp = w + 1 == W ? 0 : w + 1, wm = w == 0 ? W - 1 : w - 1;
+    const int hp = h + 1 == H ? 0 : h + 1, hm = h == 0 ? H - 1 : h - 1;
+    float* gu = gx + pair * 2 * H * W;
+    gu[(size_t)h * W + w] = (gp[(size_t)h * W + wm] - gp[(size_t)h * W + wp]) * 0.5f;
+    gu[(size_t)(H + h) * W + w] = (gp[(size_t)hp * W + w] - gp[(size_t)hm * W + w]) * 0.5f;
+  }
+}
+
+// KolmogorovFlow.upsample(mode='bilinear') (sda/mcs.py:349-359): circular pad 1 -> F.interpolate(scale r,
+// align_corners=False) -> crop r.  Output o reads padded source coordinate s = (o + 1/2) / r + 1/2 (never
+// clamped after the crop): taps floor(s) - 1 and floor(s) of the unpadded image (circular), weight frac(s).
+__device__ __forceinline__ void bilinear_taps(int o, int r, int n, int& i0, int& i1, float& lam) {
+  const float s = ((float)o + 0.5f) / (float)r + 0.5f;
+  const int f = (int)floorf(s);
+  lam = s - (float)f;
+  i0 = (f - 1 + n) % n, i1 = f % n;
+}
+
+__global__ void upsample_bilinear_kernel(const float* __restrict__ x, float* __restrict__ out, size_t n_img, int H, int W,
+                                         int r) {
+  const int Ho = H * r, Wo = W * r;
+  const size_t total = n_img * Ho * Wo;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int wo = idx % Wo, ho = (idx / Wo) % Ho;
+    const size_t img = idx / ((size_t)Wo * Ho);
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilinear_taps(ho, r, H, h0, h1, lh);
+    bilinear_taps(wo, r, W, w0, w1, lw);
+    const float* src = x + img * H * W;
+    const float top = (1.f - lw) * src[(size_t)h0 * W + w0] + lw * src[(size_t)h0 * W + w1];
+    const float bot = (1.f - lw) * src[(size_t)h1 * W + w0] + lw * src[(size_t)h1 * W + w1];
+    out[idx] = (1.f - lh) * top + lh * bot;
+  }
+}
+
+// adjoint of upsample_bilinear as a gather (deterministic): source pixel (h, w) collects the outputs whose taps
+// include it -- output rows with floor(s) - 1 == h or floor(s) == h, i.e. o in [r (h - 1/2) - 1/2 .., r (h + 3/2) - 1/2)
+__global__ void upsample_bilinear_adjoint_kernel(const float* __restrict__ g, float* __restrict__ gx, size_t n_img,
+                                                 int H, int W, int r) {
+  const int Ho = H * r, Wo = W * r;
+  const size_t total = n_img * H * W;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int w = idx % W, h = (idx / W) % H;
+    const size_t img = idx / ((size_t)W * H);
+    const float* gp = g + img * Ho * Wo;
+    float acc = 0.f;
+    // candidate outputs: the 2 r rows / columns around the pixel (circular), weights recomputed from the taps
+    for (int dh = -r; dh < 2 * r; ++dh) {
+      const int ho = ((h * r + dh) % Ho + Ho) % Ho;
+      int h0, h1;
+      float lh;
+      bilinear_taps(ho, r, H, h0, h1, lh);
+      const float wh = (h0 == h ? 1.f - lh : 0.f) + (h1 == h ? lh : 0.f);
+      if (wh == 0.f) continue;
+      for (int dw = -r; dw < 2 * r; ++dw) {
+        const int wo = ((w * r + dw) % Wo + Wo) % Wo;
+        int w0, w1;
+        float lw;
+        bilinear_taps(wo, r, W, w0, w1, lw);
+        const float ww = (w0 == w ? 1.f - lw : 0.f) + (w1 == w ? lw : 0.f);
+        if (ww != 0.f) acc += wh * ww * gp[(size_t)ho * Wo + wo];
+      }
+    }
+    gx[idx] = acc;
+  }
+}
+
 }  // namespace
 
 }  // namespace sdab
@@ -463,6 +552,41 @@ int sdab_vorticity(const float* x, float* out, size_t n_pair, int H, int W, void
   SDAB_TRY(sdab_device_check());
   vorticity_kernel<<<grid_for(n_pair * H * W), kBlock, 0, (cudaStream_t)stream>>>(x, out, n_pair, H, W);
   SDAB_LAUNCH_CHECK("vorticity_kernel");
+  return SDAB_OK;
+}
+
+int sdab_coarsen_adjoint(const float* g, float* gx, size_t n_img, int H, int W, int r, void* stream) {
+  SDAB_REQUIRE(g && gx, "null argument");
+  SDAB_REQUIRE(r >= 1 && H % r == 0 && W % r == 0, "coarsening factor must divide the image size");
+  SDAB_TRY(sdab_device_check());
+  coarsen_adjoint_kernel<<<grid_for(n_img * H * W), kBlock, 0, (cudaStream_t)stream>>>(g, gx, n_img, H, W, r);
+  SDAB_LAUNCH_CHECK("coarsen_adjoint_kernel");
+  return SDAB_OK;
+}
+
+int sdab_vorticity_adjoint(const float* g, float* gx, size_t n_pair, int H, int W, void* stream) {
+  SDAB_REQUIRE(g && gx, "null argument");
+  SDAB_TRY(sdab_device_check());
+  vorticity_adjoint_kernel<<<grid_for(n_pair * H * W), kBlock, 0, (cudaStream_t)stream>>>(g, gx, n_pair, H, W);
+  SDAB_LAUNCH_CHECK("vorticity_adjoint_kernel");
+  return SDAB_OK;
+}
+
+int sdab_upsample_bilinear(const float* x, float* out, size_t n_img, int H, int W, int r, void* stream) {
+  SDAB_REQUIRE(x && out, "null argument");
+  SDAB_REQUIRE(r >= 1 && H >= 1 && W >= 1, "invalid upsampling factor");
+  SDAB_TRY(sdab_device_check());
+  upsample_bilinear_kernel<<<grid_for(n_img * H * r * W * r), kBlock, 0, (cudaStream_t)stream>>>(x, out, n_img, H, W, r);
+  SDAB_LAUNCH_CHECK("upsample_bilinear_kernel");
+  return SDAB_OK;
+}
+
+int sdab_upsample_bilinear_adjoint(const float* g, float* gx, size_t n_img, int H, int W, int r, void* stream) {
+  SDAB_REQUIRE(g && gx, "null argument");
+  SDAB_REQUIRE(r >= 1 && H >= 2 && W >= 2, "invalid upsampling factor");
+  SDAB_TRY(sdab_device_check());
+  upsample_bilinear_adjoint_kernel<<<grid_for(n_img * H * W), kBlock, 0, (cudaStream_t)stream>>>(g, gx, n_img, H, W, r);
+  SDAB_LAUNCH_CHECK("upsample_bilinear_adjoint_kernel");
   return SDAB_OK;
 }
 

@@ -286,11 +286,17 @@ class KolmogorovFlow(MarkovChain):
         return self._run(x, length, keep=not last)
 
     # ------------------------------------------------------------------ observation helpers
+    # On CUDA fp32 tensors these run as single libsdab kernels with analytic adjoints (they are the A(x) of the
+    # guided sampler, differentiated at every score evaluation: sda/score.py:389-394); anything else takes the
+    # reference's PyTorch formulas.
     @staticmethod
     def coarsen(x: Tensor, r: int = 2) -> Tensor:
-        r"""Mean over r x r blocks.  Reference: sda/mcs.py:340-347 (differentiable PyTorch)."""
+        r"""Mean over r x r blocks.  Reference: sda/mcs.py:340-347."""
 
         *batch, h, w = x.shape
+
+        if _native_image(x) and h % r == 0 and w % r == 0:
+            return _Coarsen.apply(x, r)
 
         return x.reshape(*batch, h // r, r, w // r, r).mean(dim=(-3, -1))
 
@@ -299,6 +305,9 @@ class KolmogorovFlow(MarkovChain):
         r"""Circular-padded interpolation.  Reference: sda/mcs.py:349-359."""
 
         *batch, h, w = x.shape
+
+        if mode == 'bilinear' and _native_image(x) and h >= 3 and w >= 3 and isinstance(r, int):
+            return _Upsample.apply(x, r)
 
         x = x.reshape(-1, 1, h, w)
         x = torch.nn.functional.pad(x, pad=(1, 1, 1, 1), mode='circular')
@@ -311,8 +320,102 @@ class KolmogorovFlow(MarkovChain):
     def vorticity(x: Tensor) -> Tensor:
         r"""Central-difference curl with circular wrap.  Reference: sda/mcs.py:361-375."""
 
+        if _native_image(x) and x.dim() >= 3 and x.shape[-3] == 2:
+            return _Vorticity.apply(x)
+
         u, v = x[..., 0, :, :], x[..., 1, :, :]
         du = (torch.roll(u, -1, dims=-1) - torch.roll(u, 1, dims=-1)) / 2
         dv = (torch.roll(v, -1, dims=-2) - torch.roll(v, 1, dims=-2)) / 2
 
         return du - dv
+
+
+def _native_image(x: Tensor) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() >= 2 and x.numel() > 0
+
+
+def _call(name: str, *args) -> None:
+    _lib.check(getattr(_lib.load(), name)(*args, _lib.stream_ptr()))
+
+
+class _Coarsen(torch.autograd.Function):
+    r"""sdab_coarsen / sdab_coarsen_adjoint."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, r: int) -> Tensor:
+        *batch, h, w = x.shape
+        x = x.contiguous()
+        out = torch.empty((*batch, h // r, w // r), dtype=x.dtype, device=x.device)
+        ctx.meta = (tuple(x.shape), r)
+
+        with torch.cuda.device(x.device):
+            _call('sdab_coarsen', x.data_ptr(), out.data_ptr(), x.numel() // (h * w), h, w, r)
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        shape, r = ctx.meta
+        h, w = shape[-2:]
+        g = g.contiguous()
+        gx = torch.empty(shape, dtype=g.dtype, device=g.device)
+
+        with torch.cuda.device(g.device):
+            _call('sdab_coarsen_adjoint', g.data_ptr(), gx.data_ptr(), gx.numel() // (h * w), h, w, r)
+
+        return gx, None
+
+
+class _Upsample(torch.autograd.Function):
+    r"""sdab_upsample_bilinear / sdab_upsample_bilinear_adjoint."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, r: int) -> Tensor:
+        *batch, h, w = x.shape
+        x = x.contiguous()
+        out = torch.empty((*batch, r * h, r * w), dtype=x.dtype, device=x.device)
+        ctx.meta = (tuple(x.shape), r)
+
+        with torch.cuda.device(x.device):
+            _call('sdab_upsample_bilinear', x.data_ptr(), out.data_ptr(), x.numel() // (h * w), h, w, r)
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        shape, r = ctx.meta
+        h, w = shape[-2:]
+        g = g.contiguous()
+        gx = torch.empty(shape, dtype=g.dtype, device=g.device)
+
+        with torch.cuda.device(g.device):
+            _call('sdab_upsample_bilinear_adjoint', g.data_ptr(), gx.data_ptr(), gx.numel() // (h * w), h, w, r)
+
+        return gx, None
+
+
+class _Vorticity(torch.autograd.Function):
+    r"""sdab_vorticity / sdab_vorticity_adjoint."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor) -> Tensor:
+        *batch, _, h, w = x.shape
+        x = x.contiguous()
+        out = torch.empty((*batch, h, w), dtype=x.dtype, device=x.device)
+        ctx.shape = tuple(x.shape)
+
+        with torch.cuda.device(x.device):
+            _call('sdab_vorticity', x.data_ptr(), out.data_ptr(), x.numel() // (2 * h * w), h, w)
+
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        h, w = ctx.shape[-2:]
+        g = g.contiguous()
+        gx = torch.empty(ctx.shape, dtype=g.dtype, device=g.device)
+
+        with torch.cuda.device(g.device):
+            _call('sdab_vorticity_adjoint', g.data_ptr(), gx.data_ptr(), gx.numel() // (2 * h * w), h, w)
+
+        return gx

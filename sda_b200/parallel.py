@@ -131,4 +131,48 @@ def shard_windows(score: MCScoreNet, group=None) -> MCScoreNet:
     return score
 
 
-__all__ = ['shard_windows', 'ShardedMCScoreNet', 'window_range', 'shard_geometry']
+def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
+    r"""Data-parallel training step (BASELINE config 5; the reference trains on one GPU, sda/utils.py:136-143):
+    averages the parameter gradients of `module` over `group` after `loss.backward()`.  The convolution gradients
+    of every native `UNet` inside live in one flat buffer (`UNet._grad_flat`, written by sdab_unet_backward), which
+    is all-reduced in place with ONE collective; the remaining few gradients (projection Linears, time embedding:
+    about 1 % of the parameters) go through one coalesced all-reduce.  Same result as DistributedDataParallel's
+    averaging, without its bucket copies."""
+
+    from .nn import UNet
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+
+    world = dist.get_world_size(group)
+    covered = set()
+
+    for m in module.modules():
+        flat = getattr(m, '_grad_flat', None) if isinstance(m, UNet) else None
+
+        if flat is None:
+            continue
+
+        convs, _ = m._ordered_parameters()
+        params = [c.weight for c in convs] + [c.bias for c in convs]
+        lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * 4
+
+        # the views are only trusted while every gradient still points into the flat buffer (autograd keeps
+        # the tensors it is handed when .grad was None: optimizer.zero_grad(set_to_none=True), the default)
+        if all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in params):
+            dist.all_reduce(flat, group=group)
+            flat.div_(world)
+            covered.update(id(p) for p in params)
+
+    rest = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in covered]
+
+    if rest:
+        packed = torch.cat([g.reshape(-1) for g in rest])
+        dist.all_reduce(packed, group=group)
+        packed.div_(world)
+
+        for g, v in zip(rest, packed.split([g.numel() for g in rest])):
+            g.copy_(v.view_as(g))
+
+
+__all__ = ['shard_windows', 'ShardedMCScoreNet', 'window_range', 'shard_geometry', 'allreduce_gradients']

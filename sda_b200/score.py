@@ -577,7 +577,8 @@ class VPSDE(nn.Module):
 
                     state['draws'] += 1
                 else:
-                    z = self.noise_source(x) if self.noise_source is not None else torch.randn_like(x)
+                    # (a window-sharded sampler on this plain-PyTorch path takes rank 0's draw)
+                    z = self.noise_source(x) if self.noise_source is not None else self._from_shard_root(torch.randn_like(x))
                     eps = self.eps(x, t - dt, c)
                     delta = tau / eps.square().mean(dim=self.dims, keepdim=True)
 

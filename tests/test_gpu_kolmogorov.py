@@ -136,3 +136,62 @@ def test_kernels_reach_the_laminar_kolmogorov_flow(size):
     exact = amp * np.sin(4 * (np.arange(size) + 0.5) * h)[None, :] * np.ones((size, 1))
     assert np.abs(x[:, 0] - exact).max() < 2e-5 * amp
     assert np.abs(x[:, 1]).max() < 2e-5 * amp
+
+
+def test_observation_operators_values_and_gradients(golden):
+    r"""KolmogorovFlow.coarsen / vorticity / upsample on CUDA tensors run the libsdab kernels with analytic
+    adjoints: values against the unmodified reference's recorded outputs, values
+    and input-gradients against the reference's PyTorch formulas evaluated by autograd on the CPU."""
+
+    import torch.nn.functional as F
+
+    from sda_b200 import _lib
+    from sda_b200.mcs import KolmogorovFlow as KF
+
+    g = golden('helpers')
+    x = torch.from_numpy(g['x'])
+    assert torch.allclose(KF.coarsen(x.cuda(), 4).cpu(), torch.from_numpy(g['coarsen4']), atol=1e-6)
+    assert torch.allclose(KF.vorticity(x.cuda()).cpu(), torch.from_numpy(g['vorticity']), atol=1e-6)
+
+    if 'upsample2' in g:
+        assert torch.allclose(KF.upsample(x.cuda(), 2).cpu(), torch.from_numpy(g['upsample2']), atol=1e-6)
+
+    def ref_upsample(v, r):  # sda/mcs.py:349-359
+        *batch, h, w = v.shape
+        v = F.pad(v.reshape(-1, 1, h, w), pad=(1, 1, 1, 1), mode='circular')
+        v = F.interpolate(v, scale_factor=(r, r), mode='bilinear')[..., r:-r, r:-r]
+        return v.reshape(*batch, r * h, r * w)
+
+    def ref_vorticity(v):  # sda/mcs.py:361-375
+        *batch, _, h, w = v.shape
+        y = F.pad(v.reshape(-1, 2, h, w), pad=(1, 1, 1, 1), mode='circular')
+        (du,) = torch.gradient(y[:, 0], dim=-1)
+        (dv,) = torch.gradient(y[:, 1], dim=-2)
+        return (du - dv)[:, 1:-1, 1:-1].reshape(*batch, h, w)
+
+    def ref_coarsen(v, r):  # sda/mcs.py:340-347
+        *batch, h, w = v.shape
+        return v.reshape(*batch, h // r, r, w // r, r).mean(dim=(-3, -1))
+
+    torch.manual_seed(3)
+    cases = [
+        (lambda v: KF.coarsen(v, 4), lambda v: ref_coarsen(v, 4), (2, 3, 2, 16, 24)),
+        (lambda v: KF.coarsen(v[:, ::2], 8), lambda v: ref_coarsen(v[:, ::2], 8), (1, 5, 2, 32, 32)),  # bench.py's A
+        (KF.vorticity, ref_vorticity, (3, 2, 12, 20)),
+        (lambda v: KF.upsample(v, 2), lambda v: ref_upsample(v, 2), (2, 2, 6, 10)),
+        (lambda v: KF.upsample(v, 3), lambda v: ref_upsample(v, 3), (4, 5, 7)),
+    ]
+
+    for ours, ref, shape in cases:
+        v = torch.randn(shape)
+        vr = v.clone().requires_grad_(True)
+        out_ref = ref(vr)
+        cot = torch.randn_like(out_ref)
+        (g_ref,) = torch.autograd.grad(out_ref, vr, cot)
+        vc = v.cuda().requires_grad_(True)
+        _lib.launch_count(reset=True)
+        out = ours(vc)
+        (g_ours,) = torch.autograd.grad(out, vc, cot.cuda())
+        assert _lib.launch_count() == 2  # one forward and one adjoint kernel: the native path ran
+        assert torch.allclose(out.detach().cpu(), out_ref.detach(), atol=2e-6, rtol=1e-5)
+        assert torch.allclose(g_ours.cpu(), g_ref, atol=2e-6, rtol=1e-5)

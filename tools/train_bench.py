@@ -49,9 +49,9 @@ def main():
         opt.step()
         return l
 
-    if world > 1:
-        # DDP hooks fire on the parameter gradients produced by the native backward; VPSDE.loss is
-        # not the module's forward, so route it through a thin wrapper module
+    if world > 1 and os.environ.get('SDAB_TRAIN_DDP'):
+        # torch DDP for comparison: its hooks fire on the parameter gradients produced by the native backward;
+        # VPSDE.loss is not the module's forward, so route it through a thin wrapper module
         class Loss(torch.nn.Module):
             def __init__(self, sde):
                 super().__init__()
@@ -66,6 +66,19 @@ def main():
             l = wrapped(x)
             opt.zero_grad(set_to_none=True)
             l.backward()
+            opt.step()
+            return l
+    elif world > 1:
+        from sda_b200.parallel import allreduce_gradients
+
+        for p in sde.parameters():  # same initial weights on every rank (DDP broadcasts them too)
+            dist.broadcast(p.data, src=0)
+
+        def step():  # noqa: F811
+            l = sde.loss(x)
+            opt.zero_grad(set_to_none=True)
+            l.backward()
+            allreduce_gradients(sde)  # one in-place all-reduce of the flat convolution-gradient buffer
             opt.step()
             return l
 
@@ -96,7 +109,8 @@ def main():
         print(json.dumps({
             'workload': 'VPSDE.loss + backward + AdamW, U-Net (96, 192, 384) x (3, 3, 3), windows (10, 64, 64), '
                         f'batch 32 per GPU x {world} GPU(s)',
-            'mode': os.environ.get('SDAB_MODE', 'bf16x3'), 'n_gpus': world, 'iterations': iters,
+            'mode': os.environ.get('SDAB_MODE', 'bf16x3'), 'n_gpus': world,
+            'gradient_exchange': 'none' if world == 1 else ('torch DDP' if os.environ.get('SDAB_TRAIN_DDP') else 'flat in-place all-reduce'), 'iterations': iters,
             'ms_per_iteration': ms / iters, 'iterations_per_s': iters / (ms * 1e-3),
             'samples_per_s': 32 * world * iters / (ms * 1e-3),
             'algorithmic_tflops': 3 * 32 * world * bench.CONV_FLOP_PER_PIXEL * 64 * 64 * iters / (ms * 1e-3) / 1e12,
