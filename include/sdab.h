@@ -205,6 +205,9 @@ int sdab_randn(float* out, size_t n, uint64_t seed, uint64_t offset, void* strea
 /* Tweedie estimate and final combination of GaussianScore.forward (score.py:387,396):
  *   xhat = (x - sigma * eps) / mu ;   out = eps - sigma * s                                  */
 int sdab_tweedie(const float* x, const float* eps, float mu, float sigma, float* xhat, size_t n, void* stream);
+/* the same with mu and sigma as device scalars: the caller does not synchronise on the schedule */
+int sdab_tweedie_dev(const float* x, const float* eps, const float* mu, const float* sigma, float* xhat, size_t n,
+                     void* stream);
 int sdab_axpy(const float* a, const float* b, float alpha, float* out, size_t n, void* stream); /* out = a + alpha b */
 
 /* ------------------------------------------------------------------------- *

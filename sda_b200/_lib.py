@@ -76,6 +76,7 @@ _PROTOTYPES = {
                                    c_void_p, c_void_p]),
     'sdab_randn': (c_int, [c_void_p, c_size_t, c_uint64, c_uint64, c_void_p]),
     'sdab_tweedie': (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_size_t, c_void_p]),
+    'sdab_tweedie_dev': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'sdab_axpy': (c_int, [c_void_p, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
     # Kolmogorov
     'sdab_kolmogorov_create': (c_int, [c_int, c_double, c_double, POINTER(c_void_p)]),

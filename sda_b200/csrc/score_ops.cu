@@ -282,6 +282,14 @@ __global__ void tweedie4_kernel(const float4* __restrict__ x, const float4* __re
   }
 }
 
+// the same with mu and sigma read from device memory (no host synchronisation on the schedule scalars)
+__global__ void tweedie_dev_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ mu,
+                                   const float* __restrict__ sigma, float* __restrict__ xhat, size_t n) {
+  const float m = *mu, s = *sigma;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    xhat[i] = (x[i] - s * eps[i]) / m;
+}
+
 __global__ void axpy_kernel(const float* __restrict__ a, const float* __restrict__ b, float alpha,
                             float* __restrict__ out, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -527,6 +535,15 @@ int sdab_tweedie(const float* x, const float* eps, float mu, float sigma, float*
   else
     tweedie_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, eps, mu, sigma, xhat, n);
   SDAB_LAUNCH_CHECK("tweedie_kernel");
+  return SDAB_OK;
+}
+
+int sdab_tweedie_dev(const float* x, const float* eps, const float* mu, const float* sigma, float* xhat, size_t n,
+                     void* stream) {
+  SDAB_REQUIRE(x && eps && xhat && mu && sigma, "null argument");
+  SDAB_TRY(sdab_device_check());
+  tweedie_dev_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(x, eps, mu, sigma, xhat, n);
+  SDAB_LAUNCH_CHECK("tweedie_dev_kernel");
   return SDAB_OK;
 }
 

@@ -616,22 +616,25 @@ class SubSubVPSDE(VPSDE):
 
 # --------------------------------------------------------------------------- guidance
 class _Tweedie(torch.autograd.Function):
-    r"""x_hat = (x - sigma eps) / mu as one kernel (sdab_tweedie) with its analytic adjoint."""
+    r"""x_hat = (x - sigma eps) / mu as one kernel (sdab_tweedie_dev) with its analytic adjoint.  mu and sigma
+    stay 0-d device tensors: nothing on this path synchronises the host with the GPU."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, eps: Tensor, mu: float, sigma: float) -> Tensor:
-        ctx.coef = (mu, sigma)
+    def forward(ctx, x: Tensor, eps: Tensor, mu: Tensor, sigma: Tensor) -> Tensor:
+        mu = mu.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        sigma = sigma.detach().to(device=x.device, dtype=torch.float32).contiguous()
+        ctx.save_for_backward(mu, sigma)
         x, eps = x.contiguous(), eps.contiguous()
         out = torch.empty_like(x)
 
         with torch.cuda.device(x.device):
-            _lib.check(_lib.load().sdab_tweedie(x.data_ptr(), eps.data_ptr(), mu, sigma, out.data_ptr(), x.numel(), _lib.stream_ptr()))
+            _lib.check(_lib.load().sdab_tweedie_dev(x.data_ptr(), eps.data_ptr(), mu.data_ptr(), sigma.data_ptr(), out.data_ptr(), x.numel(), _lib.stream_ptr()))
 
         return out
 
     @staticmethod
     def backward(ctx, g: Tensor):
-        mu, sigma = ctx.coef
+        mu, sigma = ctx.saved_tensors
         gx = g / mu if ctx.needs_input_grad[0] else None
         ge = g * (-sigma / mu) if ctx.needs_input_grad[1] else None
 
@@ -640,7 +643,7 @@ class _Tweedie(torch.autograd.Function):
 
 def _tweedie(x: Tensor, eps: Tensor, mu: Tensor, sigma: Tensor) -> Tensor:
     if x.is_cuda and x.dtype == torch.float32 and eps.shape == x.shape and mu.dim() == 0 and sigma.dim() == 0:
-        return _Tweedie.apply(x, eps, float(mu), float(sigma))
+        return _Tweedie.apply(x, eps, mu, sigma)
 
     return (x - sigma * eps) / mu
 

@@ -162,3 +162,54 @@ def loop(
         )
 
         sched.step()
+
+
+# --------------------------------------------------------------------------- Lorenz evaluation helpers
+# Host-side glue of experiments/lorenz/*.py (`from sda.utils import *`), outside the accelerated path
+# (out of scope as kernel targets); plain PyTorch so that those scripts import and run.
+def random_config(configs: Dict[str, Any]) -> Dict[str, Any]:
+    r"""One random choice per key.  Reference: sda/utils.py:28-32."""
+
+    import random
+
+    return {key: random.choice(list(values)) for key, values in configs.items()}
+
+
+def bpf(x: Tensor, y: Tensor, transition, likelihood, step: int = 1) -> Tensor:
+    r"""Bootstrap particle filter: (M, *) initial particles, (N, *) observations -> (M, N * step + 1, *)
+    resampled trajectories.  Reference: sda/utils.py:168-202."""
+
+    paths = x.unsqueeze(1)
+
+    for obs in y:
+        for _ in range(step):
+            paths = torch.cat((paths, transition(paths[:, -1]).unsqueeze(1)), dim=1)
+
+        weights = likelihood(obs, paths[:, -1])
+        paths = paths[torch.multinomial(weights, weights.shape[0], replacement=True)]
+
+    return paths
+
+
+def emd(x: Tensor, y: Tensor) -> Tensor:
+    r"""Earth mover's distance between two sample sets (POT, imported on use).  Reference: sda/utils.py:205-223."""
+
+    import ot  # optional dependency of the Lorenz evaluation only
+
+    return ot.emd2(x.new_tensor(()), y.new_tensor(()), torch.cdist(x.flatten(1), y.flatten(1)))
+
+
+def mmd(x: Tensor, y: Tensor) -> Tensor:
+    r"""Empirical maximum mean discrepancy with Gaussian kernels of bandwidths 1e-3 ... 1e3.
+    Reference: sda/utils.py:226-263."""
+
+    x, y = x.flatten(1), y.flatten(1)
+    sq = lambda a, b: (a.square().sum(1, keepdim=True) + b.square().sum(1) - 2 * a @ b.T)  # noqa: E731
+    dxx, dyy, dxy = sq(x, x), sq(y, y), sq(x, y)
+    total = 0
+
+    for exponent in range(-3, 4):
+        bandwidth = 10.0 ** exponent
+        total = total + torch.exp(-dxx / bandwidth).mean() + torch.exp(-dyy / bandwidth).mean() - 2 * torch.exp(-dxy / bandwidth).mean()
+
+    return total
