@@ -84,6 +84,8 @@ def main():
         dist.init_process_group('gloo')
         dist.barrier()
 
+    wall = time.perf_counter() - t0  # slowest rank: simulation, device -> host copies and the shard file
+
     if rank == 0:
         x = np.concatenate([np.load(args.out / f'shard_{r:03d}.npy') for r in range(world)])
         i, j = int(0.8 * len(x)), int(0.9 * len(x))
@@ -95,6 +97,15 @@ def main():
             (args.out / f'shard_{r:03d}.npy').unlink()
 
         print(f'wrote {args.out}/{{train,valid,test}}.npy: {i} / {j - i} / {len(x) - j} trajectories of shape {x.shape[1:]}')
+        import json
+
+        print(json.dumps({
+            'workload': f'BASELINE config 4: KolmogorovFlow(size={args.size}, dt={args.dt}), {args.members} members x {args.length} '
+                        f'transitions x {chain.steps} inner steps, last {args.keep} kept, coarsened x{args.coarsen}',
+            'n_gpus': world, 'members_per_gpu': per, 'wall_s_simulate_and_write_shards': wall,
+            'member_inner_steps_per_s_all_gpus': args.members * args.length * chain.steps / wall,
+            'member_transitions_per_s_all_gpus': args.members * args.length / wall,
+        }))
 
 
 if __name__ == '__main__':
