@@ -433,6 +433,29 @@ def run_ours(args, rank, local_rank, world):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
 
+    if args.trace is not None:
+        # kernel-level timeline of two more steps (after everything that is timed): where the non-convolution
+        # time of a step goes (NCCL, window maps, sampler kernels, the user's A), per kernel name
+        from torch.profiler import ProfilerActivity, profile
+
+        barrier()
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            for _ in range(2):
+                x = sde.denoise_step(x, step % SCHEDULE_STEPS, state, corrections=CORRECTIONS, tau=TAU)
+                step += 1
+            torch.cuda.synchronize()
+
+        if rank == 0:
+            args.trace.parent.mkdir(parents=True, exist_ok=True)
+            rows = [(e.key, e.device_time_total / 1e3, e.count) for e in prof.key_averages() if e.device_time_total > 0]
+            rows.sort(key=lambda r: -r[1])
+            total = sum(r[1] for r in rows)
+            with open(args.trace, 'w') as f:
+                f.write(f'# torch.profiler, 2 denoising steps on rank 0 of {world}: device time per kernel (ms), total {total:.2f} ms\n')
+                for name, ms, count in rows:
+                    f.write(f'{ms:10.3f} ms {100 * ms / total:5.1f}% x{count:5d}  {name[:140]}\n')
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -508,6 +531,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline and gpu_eager_baseline legs')
     ap.add_argument('--no-secondary', action='store_true', help='skip the stepper / training measurements')
     ap.add_argument('--profile-run', action='store_true', help='for runs under ncu: one warm-up step allowed, no e2e / baseline legs (not a bench value)')
+    ap.add_argument('--trace', type=Path, default=None, help='write a torch.profiler kernel table of two extra steps (rank 0) to this file')
     ap.add_argument('--full-cpu', action='store_true', help='--impl reference: time all 60 windows (about 90 s per step)')
     ap.add_argument('--variant', default='guided', choices=sorted(VARIANTS),
                     help='guided is the BASELINE metric; the others are reported beside it (SURVEY.md section 8d)')
