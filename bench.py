@@ -491,6 +491,8 @@ def run_ours(args, rank, local_rank, world):
         'roofline': {
             'bound': 'tensor', 'kernel': 'conv_umma_patch_kernel (+ conv_umma_kernel for strided / sub-pixel layers)', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
             'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+            'traffic_source': 'profiles/conv_umma_traffic.json: DRAM bytes per convolution launch from the ncu launch list of the same command '
+                              '(not re-measured in this run: ncu cannot run inside a timed bench)',
             'note': f'algorithmic FLOPs (one multiply-add pair per product) over CUDA-event kernel time of {conv_launches.value} '
                     f'launches on rank 0; the {passes}-pass mode issues {passes}x that many tensor-core FLOPs '
                     f'(tensor-pipe fraction ~ {passes * achieved / peak:.3f})',

@@ -430,3 +430,41 @@ def test_dps_guidance_matches_the_reference_formula():
 
     dps = sc.DPSGaussianScore(y.cuda(), A=A, sde=sc.VPSDE(score, shape=()), zeta=zeta).cuda()
     assert rel_l2(dps(x.cuda(), t.cuda()), ref) < TOL
+
+
+@pytest.mark.parametrize('H, W, activation, channels, blocks', [
+    (32, 64, 'SiLU', (32, 64), (1, 2)),      # non-square images
+    (64, 16, 'SiLU', (64, 32, 96), (2, 1, 1)),  # non-monotone widths, three levels, tall images
+    (32, 32, 'ReLU', (32, 64), (2, 1)),      # ReLU blocks
+])
+def test_network_variants_against_oracle(H, W, activation, channels, blocks):
+    r"""Constructor arguments beyond the two golden configurations (sda/nn.py:94-182): non-square images,
+    ReLU, uneven block counts -- guided score and unguided score against the oracle."""
+
+    import sda_b200.score as sc
+    from oracle.testing import fill_state_
+
+    k, C = 1, 2
+    score = sc.MCScoreNet(C, order=k)
+    score.kernel = sc.ScoreUNet(
+        (2 * k + 1) * C, 0, embedding=32, hidden_channels=channels, hidden_blocks=blocks, kernel_size=3,
+        activation=getattr(torch.nn, activation), spatial=2, padding_mode='circular',
+    )
+    fill_state_(score.state_dict(), seed=77)
+    state = {kk[len('kernel.'):]: v.clone() for kk, v in score.state_dict().items()}
+    score = score.cuda()
+    x = randn((2, 5, C, H, W), seed=81)
+    y = randn((2, 5, C, H // 2, W // 2), seed=82)
+    t = torch.tensor(0.52)
+    A = lambda v: v[..., ::2, ::2]  # noqa: E731
+    mc = lambda a, b: so.fold(so.score_unet(state, so.unfold(a, k).flatten(0, 1), b, None, activation=activation)  # noqa: E731
+                              .unflatten(0, (a.shape[0], -1)), k)
+    ref_eps = mc(x, t)
+    ref = so.gaussian_score(mc, y, A, 0.1, x, t, gamma=1e-2)
+
+    with torch.no_grad():
+        eps = score(x.cuda(), t.cuda())
+
+    out = sc.GaussianScore(y.cuda(), A=A, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2).cuda()(x.cuda(), t.cuda())
+    assert rel_l2(eps, ref_eps) < TOL
+    assert rel_l2(out, ref) < TOL
