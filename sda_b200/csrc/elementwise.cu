@@ -72,35 +72,43 @@ struct FoldAdjSrc {
   }
 };
 
+// block: 128 threads = one row segment of 32 pixels.  Phase 1: coalesced plane reads (a warp = 32 consecutive
+// pixels of one channel) into smem; phase 2: one thread = 8 consecutive channels of one pixel -> one 16 B store per
+// plane and halo replica (the 32 channels of a K-block are 64 contiguous bytes of the operand layout).
 template <class Src>
-__global__ void pack_planes_kernel(const Src src, bf16* __restrict__ op, int N, int Cpad, int H, int W, int s2) {
+__global__ void __launch_bounds__(128)
+    pack_planes_kernel(const Src src, bf16* __restrict__ op, int N, int Cpad, int H, int W, int s2) {
   __shared__ float tile[kChanTile][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
   const OpShape s{N, H, W, Cpad, s2};
+  const size_t lo_off = s.lo_offset();
   for (int cb = 0; cb < Cpad; cb += kChanTile) {
     const int nc = min(kChanTile, Cpad - cb);
     __syncthreads();
-    for (int c = ty; c < nc; c += blockDim.y) {
+    for (int c = wrp; c < nc; c += 4) {
       float v = 0.f;
       const float* pl = src.plane(n, cb + c);
-      if (pl && w0 + tx < W) v = pl[(size_t)h * W + w0 + tx];
-      tile[c][tx] = v;
+      if (pl && w0 + lane < W) v = pl[(size_t)h * W + w0 + lane];
+      tile[c][lane] = v;
     }
     __syncthreads();
-    for (int px = ty; px < 32; px += blockDim.y) {
+    for (int task = tid; task < 32 * (nc >> 3); task += 128) {
+      const int px = task & 31, g = task >> 5;
       const int w = w0 + px;
       if (w >= W) continue;
-      for (int c = tx; c < nc; c += 32) {
-        bf16 hi, lo;
-        split_bf16(tile[c][px], hi, lo);
-        const size_t blk = (size_t)((cb + c) >> 5) * s.block_stride() + ((cb + c) & 31);
-        for_each_replica(h, w, H, W, [&](int hp, int wp) {
-          bf16* dst = op + op_offset(s, n, hp, wp) + blk;
-          dst[0] = hi;
-          dst[s.lo_offset()] = lo;
-        });
-      }
+      const int c = g << 3;
+      uint4 hi, lo;
+      split_bf16x2(tile[c][px], tile[c + 1][px], hi.x, lo.x);
+      split_bf16x2(tile[c + 2][px], tile[c + 3][px], hi.y, lo.y);
+      split_bf16x2(tile[c + 4][px], tile[c + 5][px], hi.z, lo.z);
+      split_bf16x2(tile[c + 6][px], tile[c + 7][px], hi.w, lo.w);
+      const size_t blk = (size_t)((cb + c) >> 5) * s.block_stride() + ((cb + c) & 31);
+      for_each_replica(h, w, H, W, [&](int hp, int wp) {
+        bf16* dst = op + op_offset(s, n, hp, wp) + blk;
+        *reinterpret_cast<uint4*>(dst) = hi;
+        *reinterpret_cast<uint4*>(dst + lo_off) = lo;
+      });
     }
   }
 }
@@ -141,24 +149,30 @@ struct FoldDst {
   }
 };
 
+// block: 128 threads = one row segment of 32 pixels.  Phase 1: one thread = 8 consecutive channels of one pixel
+// (two 16 B loads); phase 2: coalesced plane writes (a warp = 32 consecutive pixels of one channel).
 template <class Dst>
-__global__ void unpack_planes_kernel(const float* __restrict__ f, const Dst dst, int N, int Creal, int Cpad, int H,
-                                     int W) {
+__global__ void __launch_bounds__(128)
+    unpack_planes_kernel(const float* __restrict__ f, const Dst dst, int N, int Creal, int Cpad, int H, int W) {
   __shared__ float tile[kChanTile][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int w0 = blockIdx.x * 32, h = blockIdx.y, n = blockIdx.z;
   for (int cb = 0; cb < Creal; cb += kChanTile) {
     const int nc = min(kChanTile, Cpad - cb);
     __syncthreads();
-    for (int px = ty; px < 32; px += blockDim.y) {
+    for (int task = tid; task < 32 * (nc >> 3); task += 128) {
+      const int px = task & 31, c = (task >> 5) << 3;
       const int w = w0 + px;
       if (w >= W) continue;
-      for (int c = tx; c < nc; c += 32) tile[c][px] = f[(((size_t)n * H + h) * W + w) * Cpad + cb + c];
+      const float4* src = reinterpret_cast<const float4*>(f + (((size_t)n * H + h) * W + w) * Cpad + cb + c);
+      const float4 a = src[0], b = src[1];
+      tile[c][px] = a.x, tile[c + 1][px] = a.y, tile[c + 2][px] = a.z, tile[c + 3][px] = a.w;
+      tile[c + 4][px] = b.x, tile[c + 5][px] = b.y, tile[c + 6][px] = b.z, tile[c + 7][px] = b.w;
     }
     __syncthreads();
-    for (int c = ty; c < nc && cb + c < Creal; c += blockDim.y) {
+    for (int c = wrp; c < nc && cb + c < Creal; c += 4) {
       float* pl = dst.plane(n, cb + c);
-      if (pl && w0 + tx < W) pl[(size_t)h * W + w0 + tx] = tile[c][tx];
+      if (pl && w0 + lane < W) pl[(size_t)h * W + w0 + lane] = tile[c][lane];
     }
   }
 }
@@ -484,7 +498,7 @@ __global__ void copy_f32_kernel(const float* __restrict__ src, float* __restrict
 }  // namespace
 
 int pack_nchw_to_op(const float* x, bf16* op, int N, int Creal, int Cpad, int H, int W, int s2, cudaStream_t st) {
-  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  dim3 grid((W + 31) / 32, H, N), block(128);
   pack_planes_kernel<<<grid, block, 0, st>>>(NchwSrc{x, Creal, (size_t)H * W}, op, N, Cpad, H, W, s2);
   SDAB_LAUNCH_CHECK("pack_planes_kernel");
   return SDAB_OK;
@@ -492,7 +506,7 @@ int pack_nchw_to_op(const float* x, bf16* op, int N, int Creal, int Cpad, int H,
 
 int pack_windows_to_op(const float* x, const float* ctx, bf16* op, const WindowIO& w, int N, int Cpad, int H, int W,
                        cudaStream_t st) {
-  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  dim3 grid((W + 31) / 32, H, N), block(128);
   pack_planes_kernel<<<grid, block, 0, st>>>(WindowSrc{x, ctx, w, (size_t)H * W}, op, N, Cpad, H, W, 0);
   SDAB_LAUNCH_CHECK("pack_planes_kernel");
   return SDAB_OK;
@@ -500,21 +514,21 @@ int pack_windows_to_op(const float* x, const float* ctx, bf16* op, const WindowI
 
 int pack_fold_adjoint_to_op(const float* g, bf16* op, const WindowIO& w, int N, int Cpad, int H, int W,
                             cudaStream_t st) {
-  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  dim3 grid((W + 31) / 32, H, N), block(128);
   pack_planes_kernel<<<grid, block, 0, st>>>(FoldAdjSrc{g, w, (size_t)H * W}, op, N, Cpad, H, W, 0);
   SDAB_LAUNCH_CHECK("pack_planes_kernel");
   return SDAB_OK;
 }
 
 int unpack_f_to_nchw(const float* f, float* x, int N, int Creal, int Cpad, int H, int W, cudaStream_t st) {
-  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  dim3 grid((W + 31) / 32, H, N), block(128);
   unpack_planes_kernel<<<grid, block, 0, st>>>(f, NchwDst{x, Creal, (size_t)H * W}, N, Creal, Cpad, H, W);
   SDAB_LAUNCH_CHECK("unpack_planes_kernel");
   return SDAB_OK;
 }
 
 int unpack_f_fold(const float* f, float* out, const WindowIO& w, int N, int Cpad, int H, int W, cudaStream_t st) {
-  dim3 grid((W + 31) / 32, H, N), block(32, 8);
+  dim3 grid((W + 31) / 32, H, N), block(128);
   unpack_planes_kernel<<<grid, block, 0, st>>>(f, FoldDst{out, w, (size_t)H * W}, N, (2 * w.order + 1) * w.C, Cpad, H,
                                                W);
   SDAB_LAUNCH_CHECK("unpack_planes_kernel");
