@@ -468,3 +468,29 @@ def test_network_variants_against_oracle(H, W, activation, channels, blocks):
     out = sc.GaussianScore(y.cuda(), A=A, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2).cuda()(x.cuda(), t.cuda())
     assert rel_l2(eps, ref_eps) < TOL
     assert rel_l2(out, ref) < TOL
+
+
+def test_packed_weights_follow_parameter_updates():
+    r"""The bf16-packed weight copies are rebuilt after optimizer steps / load_state_dict / .to() on their own and
+    after `.data` surgery once `invalidate_packed()` is called (`.data` updates do not bump the
+    version counter the cache is keyed on)."""
+
+    score, k = build_score('net_small', 16, 'cuda')
+    net = score.kernel.network
+    x = randn((1, 5, 2, 16, 16), seed=1).cuda()
+    t = torch.tensor(0.5).cuda()
+
+    with torch.no_grad():
+        base = score(x, t).clone()
+        first = net.heads[0].weight
+        first.mul_(1.5)                       # in-place op on the parameter: version bump -> repacked
+        bumped = score(x, t).clone()
+        assert not torch.equal(base, bumped)
+        first.data.mul_(1 / 1.5)              # .data surgery: invisible to the cache key ...
+        net.invalidate_packed()               # ... until the documented call
+        restored = score(x, t).clone()
+        assert rel_l2(restored, base) < 1e-6
+        state = {kk: v.clone() for kk, v in score.state_dict().items()}
+        state['kernel.network.heads.0.weight'] = state['kernel.network.heads.0.weight'] * 2
+        score.load_state_dict(state)          # load_state_dict invalidates by itself
+        assert not torch.equal(score(x, t), restored)
