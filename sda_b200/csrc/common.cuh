@@ -211,6 +211,8 @@ struct WgradProblem {
   int ntl;
   unsigned char tl_sa[9], tl_sb[9];
   unsigned short tl_mask[9];
+  float* partial;        // tcgen05 engine: workspace for the pixel-split partial sums (summed in fixed order by a
+  size_t partial_bytes;  // second kernel); null or too small: fp32 atomics into dw (non-deterministic order)
   int x_par, g_par;  // 1 + parity image id ((row & 1) * 2 + (col & 1)) of an S2-layout x / g tensor, 0: normal layout
   int g_dh, g_dw;    // origin offset of the g tile inside its parity image
 };

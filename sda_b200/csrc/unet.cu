@@ -75,8 +75,12 @@ struct Plan {
   std::vector<size_t> gc1op, gup, gz;
   std::vector<size_t> xs2g;  // training: the tail transposes' parity operand (xs2 itself feeds the heads' wgrad)
   std::vector<size_t> hsave;  // training: act(conv1) of every block as operand tensor (input of conv2's wgrad)
+  size_t wpart = 0;           // training: pixel-split partial sums of the tcgen05 weight-gradient kernel
   size_t total;
 };
+
+// one wave of at most ~150 CTAs, each leaving 512 TMEM columns x 128 lanes of fp32 partial sums
+constexpr size_t kWgradPartialBytes = (size_t)160 * 512 * 128 * sizeof(float);
 
 size_t f_bytes(int N, int H, int W, int C) { return (size_t)N * H * W * C * sizeof(float); }
 size_t op_bytes(int N, int H, int W, int C) { return OpShape{N, H, W, C, 0}.bytes(); }
@@ -123,6 +127,7 @@ Plan make_plan(const sdab_unet* h, int N, int Nt, int H, int W, bool save, bool 
     };
     per_level(h->desc_blk);
     per_level(h->asc_blk);
+    if (train) p.wpart = a.take(kWgradPartialBytes);
     p.gout_op = a.take(op_bytes(N, H, W, round_up(h->d.out_channels, 32)));
     p.gxf = a.take(f_bytes(N, H, W, round_up(h->d.in_channels, 32)));
     for (int d = 0; d < D; ++d) {
@@ -518,6 +523,7 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     w.gF = gF, w.gOP = gOP, w.xOP = xOP, w.xF = xF, w.x_kind = x_kind, w.act = act;
     w.N = N, w.H = Ho, w.W = Wo, w.Cg = Cg, w.Cx = Cx, w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin;
     w.dw = wt->dw[ci], w.db = wt->db[ci];
+    w.partial = (float*)(ws + p.wpart), w.partial_bytes = kWgradPartialBytes;
     if (engine == SDAB_ENGINE_UMMA && wgrad_umma_supported(w)) return conv3x3_wgrad_umma(w, mode, st);
     return conv3x3_wgrad(w, st);
   };
@@ -530,6 +536,7 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     WgradProblem w{};
     w.gF = gF, w.gOP = gOP, w.xOP = xs2, w.x_kind = 0, w.act = act, w.N = N, w.H = Ho, w.W = Wo, w.Cg = C, w.Cx = Cx;
     w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin, w.dw = wt->dw[ci], w.db = wt->db[ci];
+    w.partial = (float*)(ws + p.wpart), w.partial_bytes = kWgradPartialBytes;
     if (engine == SDAB_ENGINE_UMMA && wgrad_umma_supported(w)) {
       for (int qa = 0; qa < 2; ++qa)
         for (int qb = 0; qb < 2; ++qb) {
@@ -556,6 +563,7 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
     WgradProblem w{};
     w.gF = gF, w.gOP = gS2, w.xOP = xlo, w.x_kind = 0, w.act = act, w.N = N, w.H = Hl, w.W = Wl, w.Cg = C, w.Cx = Cx;
     w.cout = h->convs[ci].cout, w.cin = h->convs[ci].cin, w.dw = wt->dw[ci], w.db = nullptr;
+    w.partial = (float*)(ws + p.wpart), w.partial_bytes = kWgradPartialBytes;
     if (engine == SDAB_ENGINE_UMMA && gS2 && wgrad_umma_supported(w)) {
       SDAB_TRY(f_channel_sum(gF, wt->db[ci], (size_t)N * 4 * Hl * Wl, C, w.cout, st));
       for (int po = 0; po < 2; ++po)

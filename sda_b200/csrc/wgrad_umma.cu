@@ -53,6 +53,7 @@ struct WParams {
   uint32_t stage_bytes, x_plane_bytes, g_plane_bytes;
   int cin, cout;
   float* dw;
+  float* part;             // split partial sums [CTA][tg][128 ci][nblk co], or null: fp32 atomics straight into dw
   int ntl;                 // tap-list entries
   uint32_t tl_shift[9];    // patch-row shift of entry e (pixels)
   uint32_t tl_mask[9];     // weight taps entry e adds into
@@ -254,7 +255,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int c0 = 0; c0 < p.nblk; c0 += 32) {
         float v[32];
         tmem_ld32(t0 + (uint32_t)(t * p.nblk + c0), v);
-        if (ci < p.cin) {
+        if (p.part) {
+          // this CTA's partial sums leave as full lines (a lane owns one input channel = one row of nblk
+          // floats); wgrad_reduce_kernel sums the pixel splits in fixed order
+          float4* dst = reinterpret_cast<float4*>(p.part + (((size_t)blockIdx.x * p.tg + t) * 128 + (q * 32 + lane)) * p.nblk + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else if (ci < p.cin) {
           for (int tap = 0; tap < 9; ++tap) {
             if (!(mask >> tap & 1u)) continue;
 #pragma unroll
@@ -273,6 +280,31 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// dw[co][ci][tap] += sum over the pixel splits (in split order: deterministic) of the partial sums the CTAs of
+// one wgrad_umma_kernel launch left behind, for every weight tap the tap-list entries feed.  One thread per
+// (ci, co), co fastest: the partial reads are coalesced, the thread's nine taps are contiguous in dw.
+__global__ void wgrad_reduce_kernel(const WParams p) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.cin * p.cout) return;
+  const int co = idx % p.cout, ci = idx / p.cout;
+  const int mb = ci >> 7, nb = co / p.nblk;
+  const size_t row = (size_t)(ci & 127) * p.nblk + (co - nb * p.nblk);
+  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int e = 0; e < p.ntl; ++e) {
+    const int tgi = e / p.tg, t = e - tgi * p.tg;
+    const size_t cta0 = ((size_t)(tgi * p.nmb + mb) * p.nnb + nb) * p.splits;
+    float sum = 0.f;
+    for (int sp = 0; sp < p.splits; ++sp) sum += p.part[((cta0 + sp) * p.tg + t) * 128 * p.nblk + row];
+    const uint32_t mask = p.tl_mask[e];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+      if (mask >> tap & 1u) acc[tap] += sum;
+  }
+  float* dst = p.dw + ((size_t)co * p.cin + ci) * 9;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) dst[tap] += acc[tap];
 }
 
 // db[c] += sum over the interior pixels of an operand tensor (hi + lo)
@@ -361,6 +393,9 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   p.splits = (waves_x2 * 74 + units - 1) / units;
   if (p.splits > p.num_tiles) p.splits = p.num_tiles;
   p.cin = c.cin, p.cout = c.cout, p.dw = c.dw;
+  // split partial sums in the caller's workspace when it is large enough, fp32 atomics otherwise
+  const size_t part_bytes = (size_t)units * p.splits * p.tg * 128 * p.nblk * sizeof(float);
+  p.part = (c.partial && c.partial_bytes >= part_bytes) ? c.partial : nullptr;
 
   CUtensorMap tmX, tmG;
   // A tensor in the S2 layout holds an image of twice the sub-problem resolution as four parity images of
@@ -400,6 +435,10 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   else
     wgrad_umma_kernel<1, 16><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
+  if (p.part) {
+    wgrad_reduce_kernel<<<(p.cin * p.cout + 255) / 256, 256, 0, stream>>>(p);
+    SDAB_LAUNCH_CHECK("wgrad_reduce_kernel");
+  }
   if (c.db) {
     const int rows = c.N * c.H, rpb = (rows + 148 * 16 - 1) / (148 * 16);
     op_channel_sum_kernel<<<(rows + rpb - 1) / rpb, c.Cg, 0, stream>>>(c.gOP, c.db, c.N, c.H, c.W, c.Cg, c.cout, rpb);
