@@ -282,44 +282,77 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
-// dw[co][ci][tap] += sum over the pixel splits (in split order: deterministic) of the partial sums the CTAs of
-// one wgrad_umma_kernel launch left behind, for every weight tap the tap-list entries feed.  One thread per
-// (ci, co), co fastest: the partial reads are coalesced, the thread's nine taps are contiguous in dw.
+// dw[co][ci][tap] += sum over the pixel splits (fixed order: deterministic) of the partial sums the CTAs of one
+// wgrad_umma_kernel launch left behind, for every weight tap the tap-list entry feeds.  One thread per
+// (entry, ci, co), co fastest: the partial reads are coalesced; four independent accumulators keep loads in flight.
 __global__ void wgrad_reduce_kernel(const WParams p) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.cin * p.cout) return;
-  const int co = idx % p.cout, ci = idx / p.cout;
+  if (idx >= p.ntl * p.cin * p.cout) return;
+  const int co = idx % p.cout, ci = (idx / p.cout) % p.cin, e = idx / (p.cout * p.cin);
   const int mb = ci >> 7, nb = co / p.nblk;
-  const size_t row = (size_t)(ci & 127) * p.nblk + (co - nb * p.nblk);
-  float acc[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int e = 0; e < p.ntl; ++e) {
-    const int tgi = e / p.tg, t = e - tgi * p.tg;
-    const size_t cta0 = ((size_t)(tgi * p.nmb + mb) * p.nnb + nb) * p.splits;
-    float sum = 0.f;
-    for (int sp = 0; sp < p.splits; ++sp) sum += p.part[((cta0 + sp) * p.tg + t) * 128 * p.nblk + row];
-    const uint32_t mask = p.tl_mask[e];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
-      if (mask >> tap & 1u) acc[tap] += sum;
+  const int tgi = e / p.tg, t = e - tgi * p.tg;
+  const size_t stride = (size_t)p.tg * 128 * p.nblk;
+  const float* src = p.part + (((size_t)(tgi * p.nmb + mb) * p.nnb + nb) * p.splits * p.tg + t) * 128 * p.nblk +
+                     (size_t)(ci & 127) * p.nblk + (co - nb * p.nblk);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sp = 0;
+  for (; sp + 4 <= p.splits; sp += 4) {
+    s0 += src[(size_t)sp * stride], s1 += src[(size_t)(sp + 1) * stride];
+    s2 += src[(size_t)(sp + 2) * stride], s3 += src[(size_t)(sp + 3) * stride];
   }
+  for (; sp < p.splits; ++sp) s0 += src[(size_t)sp * stride];
+  const float sum = (s0 + s1) + (s2 + s3);
+  const uint32_t mask = p.tl_mask[e];
   float* dst = p.dw + ((size_t)co * p.cin + ci) * 9;
-#pragma unroll
-  for (int tap = 0; tap < 9; ++tap) dst[tap] += acc[tap];
+  // the taps of different entries are disjoint in every tap list unet.cu builds; atomics keep overlapping
+  // masks correct too (one addend per element and launch otherwise, so the result stays deterministic)
+  for (int tap = 0; tap < 9; ++tap)
+    if (mask >> tap & 1u) atomicAdd(dst + tap, sum);
 }
 
-// db[c] += sum over the interior pixels of an operand tensor (hi + lo)
-__global__ void op_channel_sum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int N, int H, int W, int C,
-                                      int cout, int rows_per_block) {
+// db[c] += sum over the interior pixels of an operand tensor (hi + lo).  grid: (row groups, C / 32); block: 256
+// threads = 64 pixels x 4 groups of 8 channels, 16-byte loads (the 32 channels of a K-block are 64 contiguous
+// bytes per pixel); the block's partial sums meet in shared memory and leave as 32 atomics.
+__global__ void __launch_bounds__(256)
+    op_channel_sum_kernel(const bf16* __restrict__ g, float* __restrict__ db, int N, int H, int W, int C, int cout,
+                          int rows_per_block) {
+  __shared__ float red[8][32];
   const OpShape s{N, H, W, C, 0};
-  const int c = threadIdx.x;  // blockDim.x == C
+  const int tid = threadIdx.x, sub = tid & 3, px = tid >> 2, chunk = blockIdx.y;
   const int r0 = blockIdx.x * rows_per_block, r1 = min(N * H, r0 + rows_per_block);
-  float sum = 0.f;
+  const size_t lo_off = s.lo_offset();
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int r = r0; r < r1; ++r) {
     const int n = r / H, h = r % H;
-    const bf16* row = g + op_offset(s, n, h + 1, 1) + (size_t)(c >> 5) * s.block_stride() + (c & 31);
-    for (int w = 0; w < W; ++w) sum += __bfloat162float(row[(size_t)w * 32]) + __bfloat162float(row[(size_t)w * 32 + s.lo_offset()]);
+    const bf16* row = g + op_offset(s, n, h + 1, 1) + (size_t)chunk * s.block_stride() + sub * 8;
+    for (int w = px; w < W; w += 64) {
+      const uint4 a = *reinterpret_cast<const uint4*>(row + (size_t)w * 32);
+      const uint4 b = *reinterpret_cast<const uint4*>(row + (size_t)w * 32 + lo_off);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
+        acc[2 * k + 1] += __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
+      }
+    }
   }
-  if (c < cout) atomicAdd(db + c, sum);
+  // lanes with equal `sub` hold the same 8 channels: fold the 8 pixels of a warp, then the 8 warps
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v = acc[j];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if ((tid & 31) < 4) red[tid >> 5][sub * 8 + j] = v;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) v += red[wq][tid];
+    const int c = chunk * 32 + tid;
+    if (c < cout) atomicAdd(db + c, v);
+  }
 }
 
 PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -436,12 +469,14 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
     wgrad_umma_kernel<1, 16><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
   if (p.part) {
-    wgrad_reduce_kernel<<<(p.cin * p.cout + 255) / 256, 256, 0, stream>>>(p);
+    wgrad_reduce_kernel<<<(p.ntl * p.cin * p.cout + 255) / 256, 256, 0, stream>>>(p);
     SDAB_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   if (c.db) {
-    const int rows = c.N * c.H, rpb = (rows + 148 * 16 - 1) / (148 * 16);
-    op_channel_sum_kernel<<<(rows + rpb - 1) / rpb, c.Cg, 0, stream>>>(c.gOP, c.db, c.N, c.H, c.W, c.Cg, c.cout, rpb);
+    const int chunks = c.Cg / 32, rows = c.N * c.H;
+    const int groups = (148 * 8 + chunks - 1) / chunks, rpb = (rows + groups - 1) / groups;
+    op_channel_sum_kernel<<<dim3((rows + rpb - 1) / rpb, chunks), 256, 0, stream>>>(c.gOP, c.db, c.N, c.H, c.W, c.Cg,
+                                                                                    c.cout, rpb);
     SDAB_LAUNCH_CHECK("op_channel_sum_kernel");
   }
   return SDAB_OK;
