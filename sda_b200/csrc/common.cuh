@@ -182,6 +182,7 @@ struct ConvProblem {
   int stride;          // 1 or 2
   int mode;            // SDAB_MODE_*
   int in_s2;           // input operand in the parity layout of a (2H) x (2W) image (implied by stride == 2)
+  int in_strided;      // tcgen05 engine: ... but `in` is the NORMAL layout of that image, read with a TMA element stride of 2
   ConvTaps taps;       // explicit taps (tcgen05 engine only), or n == 0
   int wtaps;           // taps in the packed weight array (0 means 9)
   int os, oh0, ow0;    // output placement (tcgen05 engine only): GEMM pixel (h, w) is pixel (os h + oh0, os w + ow0)

@@ -61,7 +61,8 @@ struct UmmaParams {
   int stages, acc_stages;
   int CB, nb;      // N of one MMA, number of N halves
   uint32_t b_plane_bytes, stage_bytes;
-  int in_s2;       // A operand in the parity layout
+  int in_s2;       // A operand addressed by parity image (stride-2 layers)
+  int in_strided;  // ... of the NORMAL layout through a TMA element stride of 2 (no parity copy exists)
   int ntaps;
   uint32_t tap[16];  // ca | cb << 8 | cp << 16 | wtap << 24
   int os, oh0, ow0, Ho, Wo;  // output placement (ConvProblem::os ...) and output image size
@@ -884,13 +885,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     // also receives the peer's bytes
     const int cbh = CTA2 ? p.CB / 2 : p.CB;  // B rows of one N half held by this CTA
     const uint32_t tx_bytes = (CTA2 ? 2u : 1u) * PLANES * (kABytes + (uint32_t)(NB * cbh) * 64u);
-    const bool s1 = !p.in_s2;
+    const bool s1 = !p.in_s2 || p.in_strided;
     for (int tile = tile_begin; tile < tile_end; tile += gridDim.x) {
       int n0, h0, w0;
       p.g.tile_origin(tile, n0, h0, w0);
       for (int tap = 0; tap < p.ntaps; ++tap) {
         const uint32_t tp = p.tap[tap];
-        const int ch = h0 + (int)(tp & 255u), cw = w0 + (int)((tp >> 8) & 255u), cp = (int)((tp >> 16) & 255u);
+        int ch = h0 + (int)(tp & 255u), cw = w0 + (int)((tp >> 8) & 255u);
+        const int cp = (int)((tp >> 16) & 255u);
+        // pixel (i, j) of parity image (pr, pc) is padded pixel (2 i + pr, 2 j + pc) of the normal layout: with an
+        // element stride of 2 in the tensor map the same box is read from there
+        if (p.in_strided) ch = 2 * ch + (cp >> 1), cw = 2 * cw + (cp & 1);
         int brow = (int)(tp >> 24) * p.nchunk * 2 * p.Cout;
         for (int chunk = 0; chunk < p.nchunk; ++chunk, brow += 2 * p.Cout) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -1258,10 +1263,12 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 int encode(CUtensorMap* map, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
            const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_64B) {
+           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_64B, const cuuint32_t* element_strides = nullptr) {
   auto fn = get_encode();
   if (!fn) return fail(SDAB_ERR_DEVICE, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (element_strides)
+    for (int i = 0; i < rank; ++i) estr[i] = element_strides[i];
   CUresult r = fn(map, dtype, rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1289,6 +1296,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(c.stride == 1 || c.stride == 2, "stride must be 1 or 2");
   p.N = c.N, p.H = c.H, p.W = c.W, p.Cin = c.Cin, p.Cout = c.Cout, p.stride = c.stride;
   p.in_s2 = c.stride == 2 || c.in_s2;
+  p.in_strided = p.in_s2 && c.in_strided;
   p.os = c.os ? c.os : 1, p.oh0 = c.oh0, p.ow0 = c.ow0;
   SDAB_REQUIRE((p.os == 1 && !p.oh0 && !p.ow0) || (p.os == 2 && p.oh0 >= 0 && p.oh0 < 2 && p.ow0 >= 0 && p.ow0 < 2),
                "invalid output placement");
@@ -1373,7 +1381,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5], strides[4];
-    if (!p.in_s2) {
+    if (!p.in_s2 || p.in_strided) {
       dims[0] = 32, dims[1] = Wp, dims[2] = Hp, dims[3] = Q, dims[4] = (cuuint64_t)c.N;
       strides[0] = 64, strides[1] = Wp * 64, strides[2] = Hp * Wp * 64, strides[3] = Q * Hp * Wp * 64;
     } else {
@@ -1383,9 +1391,12 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
       strides[3] = Q * Hp * Wp * 64;
     }
     // patch kernel: the haloed (BW + 2) x (BH + 2) patch of one image
-    const cuuint32_t box[5] = {32, (cuuint32_t)(p.patch ? kPatchW : p.g.BW), (cuuint32_t)(p.patch ? kPatchH : p.g.BH), 1,
-                               (cuuint32_t)p.g.BN};
-    SDAB_TRY(encode(&tmA, c.in, 5, dims, strides, box));
+    // (strided: the box spans 2 BW - 1 x 2 BH - 1 pixels of the tensor, every second one is traversed)
+    const cuuint32_t sx = p.in_strided ? 2 : 1;
+    const cuuint32_t box[5] = {32, sx * (cuuint32_t)(p.patch ? kPatchW : p.g.BW) - (sx - 1),
+                               sx * (cuuint32_t)(p.patch ? kPatchH : p.g.BH) - (sx - 1), 1, (cuuint32_t)p.g.BN};
+    const cuuint32_t estr[5] = {1, sx, sx, 1, 1};
+    SDAB_TRY(encode(&tmA, c.in, 5, dims, strides, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, estr));
   }
   {
     const cuuint64_t dims[2] = {32, (cuuint64_t)wtaps * p.nchunk * 2 * c.Cout};

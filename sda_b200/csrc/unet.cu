@@ -12,6 +12,7 @@
 // Heads (stride 2) read the parity layout; their transpose is a stride-1 conv over the
 // zero-upsampled cotangent.  Tails are LN -> nearest x2 -> conv; their transpose is conv^T -> 2x2
 // sum-pool -> LN^T.
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -334,6 +335,12 @@ int forward_impl(sdab_unet* h, const float* x, const float* y, int Nt, int N, in
   // convolution that produces the residual stream (ConvEpilogue::ln == 1): `prenorm` is the block
   // whose operand has already been produced that way.
   const bool fuse = engine == SDAB_ENGINE_UMMA;
+  // The stride-2 heads read their input as parity images.  Outside training the tcgen05 engine takes them straight
+  // from the normal operand layout with a TMA element stride of 2 (the epilogue of the level's last convolution
+  // writes that operand), so no parity copy (f_to_operand, one extra pass over the level) is made; training keeps
+  // the parity copy because the heads' weight-gradient kernel consumes it.
+  static const int strided_env = getenv("SDAB_STRIDED_TMA") ? atoi(getenv("SDAB_STRIDED_TMA")) : 1;
+  const bool strided = fuse && save != 2 && strided_env;
   int prenorm = -1;
   auto level_of = [&](int j) {  // level of block j
     for (int d = 0; d < D; ++d) {
@@ -393,8 +400,10 @@ int forward_impl(sdab_unet* h, const float* x, const float* y, int Nt, int N, in
       ConvProblem q{};
       q.in = d == 0 ? OP(p.in_op) : OP(p.xs2[d - 1]);
       q.wpk = wf(ci), q.N = N, q.H = Hd, q.W = Wd, q.Cin = h->convs[ci].kf, q.Cout = C, q.stride = d == 0 ? 1 : 2;
+      q.in_strided = d > 0 && strided;
       q.mode = mode, q.epi.bias = bias(ci);
       q.epi.outF = nb == 0 ? F(p.skip[d]) : F(p.x0[d]);
+      if (nb == 0 && d < D - 1 && strided) q.epi.outOP = OP(p.xs2[d]);  // operand of the next head
       fuse_ln(q, nb > 0 ? h->desc_blk[d][0] : -1);
       SDAB_TRY(run_conv(engine, q, st, h->convs[ci].cin));
       cur = q.epi.outF;
@@ -402,10 +411,12 @@ int forward_impl(sdab_unet* h, const float* x, const float* y, int Nt, int N, in
     for (int b = 0; b < nb; ++b) {
       float* dst = b == nb - 1 ? F(p.skip[d]) : (cur == F(p.x0[d]) ? F(p.x1[d]) : F(p.x0[d]));
       const int next_j = b + 1 < nb ? h->desc_blk[d][b + 1] : (d == D - 1 ? h->asc_blk[d][0] : -1);
-      SDAB_TRY(block(d, h->desc_blk[d][b], h->desc_c1[d][b], cur, dst, nullptr, next_j));
+      // the last block of a level that feeds a head also leaves its output as that head's operand
+      bf16* head_op = (b == nb - 1 && d < D - 1 && strided) ? OP(p.xs2[d]) : nullptr;
+      SDAB_TRY(block(d, h->desc_blk[d][b], h->desc_c1[d][b], cur, dst, head_op, next_j));
       cur = dst;
     }
-    if (d < D - 1) SDAB_TRY(f_to_operand(cur, OP(p.xs2[d]), N, Hd, Wd, C, 1, st));
+    if (d < D - 1 && !strided) SDAB_TRY(f_to_operand(cur, OP(p.xs2[d]), N, Hd, Wd, C, 1, st));
   }
   for (int d = D - 1; d >= 0; --d) {
     const int Hd = H >> d, Wd = W >> d, C = h->d.hidden_channels[d];
@@ -652,10 +663,15 @@ int backward_impl(sdab_unet* h, const float* gout, float* gx, void* workspace, s
       const int ci = h->tail_conv[d + 1];
       const int Cn = h->d.hidden_channels[d + 1];
       // tail conv: output cotangent = cur, input = nearest x2 of the saved low-resolution LayerNorm output
-      SDAB_TRY(f_to_operand(cur, OP(p.xs2g[d]), N, Hd, Wd, C, 1, st));
+      // (outside training the parity images are read from cur's operand GOP(d) with a TMA element stride of 2)
+      if (wt || !(getenv("SDAB_STRIDED_TMA") ? atoi(getenv("SDAB_STRIDED_TMA")) : 1))
+        SDAB_TRY(f_to_operand(cur, OP(p.xs2g[d]), N, Hd, Wd, C, 1, st));
       SDAB_TRY(wgrad_tail(ci, cur, OP(p.xs2g[d]), C, OP(p.upop[d + 1]), Cn, Hd / 2, Wd / 2));
       ConvProblem q{};
-      q.in = OP(p.xs2g[d]), q.in_s2 = 1, q.wpk = (const bf16*)(pk + h->convs[ci].off_tb), q.wtaps = 16;
+      static const int strided_env = getenv("SDAB_STRIDED_TMA") ? atoi(getenv("SDAB_STRIDED_TMA")) : 1;
+      const bool parity_copy = wt || !strided_env;
+      q.in = parity_copy ? OP(p.xs2g[d]) : GOP(d), q.in_s2 = 1, q.in_strided = parity_copy ? 0 : 1;
+      q.wpk = (const bf16*)(pk + h->convs[ci].off_tb), q.wtaps = 16;
       q.N = N, q.H = Hd / 2, q.W = Wd / 2, q.Cin = C, q.Cout = Cn, q.stride = 1, q.mode = mode;
       q.taps.n = 16;
       for (int t = 0; t < 16; ++t) {

@@ -311,7 +311,9 @@ def _score_windows(kernel: 'ScoreUNet', wb: WindowBatch, t: Tensor, c) -> Tensor
     if c is not None:
         # the context must be one stack of planes shared by every window (the forcing channel of
         # LocalScoreUNet); anything else goes through the materialised windows
-        if c.dim() < 2 or tuple(c.shape[-2:]) != (H, W) or c.numel() != c.shape[-3 if c.dim() > 2 else -2] * H * W or c.requires_grad:
+        shared = c.dim() >= 3 and tuple(c.shape[-2:]) == (H, W) and all(d == 1 for d in c.shape[:-3])
+
+        if not shared or c.requires_grad:
             xw = wb.materialize()
             return MCScoreNet.fold(ScoreUNet.forward(kernel, xw, t, c), wb.order)
 
