@@ -135,10 +135,7 @@ def test_config_network_against_oracle_at_64():
     guided = sc.GaussianScore(y.cuda(), A=A, std=0.1, sde=sc.VPSDE(score, shape=()), gamma=1e-2).cuda()
     out = guided(x.cuda(), t.cuda())
     assert rel_l2(eps, ref_eps) < TOL
-    # ReLU's derivative is a step: a pre-activation within the 5e-6 forward error of zero flips its whole
-    # gradient contribution (a fraction ~5e-6 of the units, i.e. ~sqrt(5e-6) in relative L2), so the guided score of
-    # a ReLU network is compared at 5e-3.  The Kolmogorov configuration of the reference uses SiLU (smooth).
-    assert rel_l2(out, ref) < (5e-3 if activation == 'ReLU' else TOL)
+    assert rel_l2(out, ref) < TOL
 
 
 def test_batch_invariance_and_per_sample_time():
