@@ -72,6 +72,8 @@ struct UmmaParams {
   int patch;       // patch kernel: one haloed input patch per K-block serves all nine taps
   int a_stages;    // patch kernel: depth of the patch ring (`stages` is the depth of the weight ring)
   uint32_t b_stage_bytes;
+  int nsplit;      // patch kernel, C_out > 256 without LayerNorm: a work item is (tile, half of the output channels)
+  int item_chunks; // 32-channel blocks of one work item (out_chunks / nsplit)
   int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
   uint32_t ctrl_bytes;  // control block in front of the staging tiles (barriers, TMEM slot, csplit statistics exchange)
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
@@ -330,6 +332,21 @@ __device__ __forceinline__ void load32_hilo(const bf16* __restrict__ hi, const b
 }
 
 
+// Work items of the CTA-pair kernels.  The loop index vt runs over "virtual tiles": pair-item v = vt >> 1 of CTA
+// vt & 1 of the pair.  With nsplit == 1 an item is a tile (vt IS the tile index); with nsplit == 2 the pair-item
+// v is half `v % 2` of the output channels of tile pair v / 2 -- twice as many, half as long items: the two
+// accumulator stages overlap MMAs and epilogue even at C_out = 384 (a single 384-column accumulator cannot),
+// and a short launch (a few hundred tiles on 74 pairs) wastes half as much of its last wave.
+__device__ __forceinline__ void item_of(const UmmaParams& p, int vt, int& tile, int& nh) {
+  if (p.nsplit == 1) {
+    tile = vt, nh = 0;
+  } else {
+    const int v = vt >> 1, pt = v / p.nsplit;
+    nh = v - pt * p.nsplit;
+    tile = 2 * pt + (vt & 1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ epilogue
 // Epilogue role (warps 2..5 of both kernels) of the convolutions without a fused LayerNorm: TMEM -> registers ->
 // fused bias / residual / activation / activation-derivative / bf16 split -> staged TMA stores.
@@ -351,9 +368,15 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
   const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
   int it = wg;
   int sbuf = 0;  // staging set of the next 32-channel block (running over tiles)
-  for (int tile = tile_begin + wg * (int)gridDim.x; tile < tile_end; tile += nwg * (int)gridDim.x, it += nwg) {
+  const int v_end = ((p.g.num_tiles + 1) >> 1) * p.nsplit;  // pair-items (nsplit > 1: CTA-pair patch kernel only)
+  auto in_range = [&](int vt) { return p.nsplit > 1 ? (vt >> 1) < v_end : vt < tile_end; };
+  const int nchunks = p.item_chunks;
+  for (int vt = tile_begin + wg * (int)gridDim.x; in_range(vt); vt += nwg * (int)gridDim.x, it += nwg) {
     const int acc = it % p.acc_stages;
     const uint32_t acc_phase = (it / p.acc_stages) & 1;
+    int tile, nh;
+    item_of(p, vt, tile, nh);
+    const int gc0 = nh * nchunks;  // first 32-channel block of this item in the output tensor
     int n0, h0, w0;
     p.g.tile_origin(tile, n0, h0, w0);
     // (h, w): output pixel of this thread in the (Ho x Wo) output image (ConvProblem::os, oh0, ow0)
@@ -382,27 +405,30 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
       // developer ablation bits: 16 = no global operand loads, 32 = no stores
       const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
       {
-        // pull the next tile's epilogue operands of this pixel row into L2 one tile ahead
-        const int nt = tile + nwg * (int)gridDim.x;
-        if (nt < p.g.num_tiles) {
+        // pull the next item's epilogue operands of this pixel row into L2 one item ahead
+        const int nvt = vt + nwg * (int)gridDim.x;
+        int nt, nnh;
+        item_of(p, nvt, nt, nnh);
+        if (in_range(nvt) && nt < p.g.num_tiles) {
           int nn0, nh0, nw0;
           p.g.tile_origin(nt, nn0, nh0, nw0);
-          const int nn = nn0 + bn, nh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
+          const int nn = nn0 + bn, nhh = p.os * (nh0 + bh) + p.oh0, nw = p.os * (nw0 + bw) + p.ow0;
           if (nn < p.N) {
-            const size_t npix = ((size_t)nn * p.Ho + nh) * p.Wo + nw;
+            const size_t npix = ((size_t)nn * p.Ho + nhh) * p.Wo + nw;
             const float* pf = p.epi.res ? p.epi.res : p.epi.dact;
             if (pf)
-              for (int c = 0; c < p.Cout; c += 32) prefetch_l2(pf + npix * p.Cout + c);
+              for (int c = 0; c < nchunks; ++c) prefetch_l2(pf + npix * p.Cout + (nnh * nchunks + c) * 32);
           }
         }
       }
-      for (int cc = cc0; cc < p.out_chunks; cc += ccstep) {
+      for (int cc = cc0; cc < nchunks; cc += ccstep) {
+        const int gc = gc0 + cc;  // block index in the output tensor; cc indexes the accumulator columns
         float v[32], f[32], rr[32];
         // operands from global memory first: their latency overlaps the accumulator load
-        if (has_res) load32(p.epi.res + pix * p.Cout + cc * 32, rr);
-        if (has_dact) load32(p.epi.dact + pix * p.Cout + cc * 32, rr);
+        if (has_res) load32(p.epi.res + pix * p.Cout + gc * 32, rr);
+        if (has_dact) load32(p.epi.dact + pix * p.Cout + gc * 32, rr);
         tmem_ld32(t0 + cc * 32, v);
-        if (cc + ccstep >= p.out_chunks) {
+        if (cc + ccstep >= nchunks) {
           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -413,7 +439,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
               mbar_arrive(bar_tempty + 8 * acc);
           }
         }
-        epilogue_math32(p.epi, v, f, rr, has_res, has_dact, cc * 32);
+        epilogue_math32(p.epi, v, f, rr, has_res, has_dact, gc * 32);
         if (p.debug & 32) continue;
         // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
         const uint32_t staging = staging0 + sbuf * kStagingBytes;
@@ -446,7 +472,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           }
           if (edge) {
             // halo replicas of edge pixels (the TMA box covers the interior position only)
-            const size_t blk = (size_t)cc * so.block_stride(), lo_off = so.lo_offset();
+            const size_t blk = (size_t)gc * so.block_stride(), lo_off = so.lo_offset();
             bool first = true;
             for_each_replica(h, w, p.Ho, p.Wo, [&](int hp, int wp) {
               if (first) {
@@ -469,10 +495,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
           // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
           // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
-          if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
+          if (wantF) tma_store_3d(&tmF, staging, gc * 32, w0, n0 * p.H + h0);
           if (wantO) {
-            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
-            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + cc, n0);
+            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, gc, n0);
+            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -1096,6 +1122,8 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
 
   const uint32_t acc_stride = p.acc_stages == 2 ? 256u : 0u;
   const int cbh = CTA2 ? p.CB / 2 : p.CB;  // B rows of one N half held by this CTA
+  // pair-items of this launch (item_of); for nsplit == 1 "(vt >> 1) < v_end" is "tile < tile_end"
+  const int v_end = ((p.g.num_tiles + 1) >> 1) * p.nsplit;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -1105,10 +1133,11 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     const uint32_t b_tx = (CTA2 ? 2u : 1u) * PLANES * (uint32_t)(NB * cbh) * 64u;
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
-    int a_tile = tile_begin, a_chunk = 0;  // cursor of the patch ring
+    int a_vt = tile_begin, a_chunk = 0;  // cursor of the patch ring (virtual tile = work item, item_of)
     auto issue_patch = [&]() {
-      if (a_tile >= tile_end) return;
-      int n0, h0, w0;
+      if ((a_vt >> 1) >= v_end) return;
+      int a_tile, a_nh, n0, h0, w0;
+      item_of(p, a_vt, a_tile, a_nh);
       p.g.tile_origin(a_tile, n0, h0, w0);
       mbar_wait(bar_aempty + 8 * as, aph ^ 1);
       if (elect_one()) {
@@ -1125,10 +1154,12 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
       }
       __syncwarp();
       if (++as == p.a_stages) as = 0, aph ^= 1;
-      if (++a_chunk == p.nchunk) a_chunk = 0, a_tile += gridDim.x;
+      if (++a_chunk == p.nchunk) a_chunk = 0, a_vt += gridDim.x;
     };
     issue_patch();
-    for (int tile = tile_begin; tile < tile_end; tile += gridDim.x) {
+    for (int vt = tile_begin; (vt >> 1) < v_end; vt += gridDim.x) {
+      int tile, nh;
+      item_of(p, vt, tile, nh);
       for (int chunk = 0; chunk < p.nchunk; ++chunk) {
         issue_patch();
         for (int tap = 0; tap < 9; ++tap) {
@@ -1143,7 +1174,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
 #pragma unroll
               for (int half = 0; half < NB; ++half) {
                 const uint32_t dst = sb + pl * p.b_plane_bytes + half * cbh * 64;
-                const int row = brow + pl * p.Cout + half * p.CB + (CTA2 ? (int)rank * cbh : 0);
+                const int row = brow + pl * p.Cout + (nh + half) * p.CB + (CTA2 ? (int)rank * cbh : 0);
                 if constexpr (CTA2)
                   tma_load_2d_2sm(dst, &tmB, full, 0, row);
                 else
@@ -1168,7 +1199,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     int it = 0;
-    for (int tile = tile_begin; leader && tile < tile_end; tile += gridDim.x, ++it) {
+    for (int vt = tile_begin; leader && (vt >> 1) < v_end; vt += gridDim.x, ++it) {
       const int acc = it % p.acc_stages;
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -1318,18 +1349,29 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   const int wtaps = c.wtaps ? c.wtaps : 9;
   p.nchunk = c.Cin / 32;
   p.planes = c.mode == SDAB_MODE_BF16X3 ? 2 : 1;
+  static const int cta2_env = getenv("SDAB_UMMA_CTA2") ? atoi(getenv("SDAB_UMMA_CTA2")) : 1;
+  const bool cta2 = cta2_env != 0 && c.Cout % 32 == 0;  // each CTA holds C_out / 2 weight rows (multiple of 16)
+  static const int patch_env = getenv("SDAB_UMMA_PATCH") ? atoi(getenv("SDAB_UMMA_PATCH")) : 1;
+  static const int nsplit_env = getenv("SDAB_UMMA_NSPLIT") ? atoi(getenv("SDAB_UMMA_NSPLIT")) : 1;
+  const bool patch_ok = patch_env && cta2 && c.Cout % 32 == 0 && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 &&
+                        p.os == 1 && c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
+  p.nsplit = 1;
   if (c.Cout <= 256) {
     p.CB = c.Cout, p.nb = 1, p.acc_stages = 2;
   } else {
     SDAB_REQUIRE(c.Cout % 32 == 0, "C_out above 256 must be a multiple of 32");
-    p.CB = c.Cout / 2, p.nb = 2, p.acc_stages = 1;
+    if (patch_ok && nsplit_env && !c.epi.ln && c.Cout % 64 == 0) {
+      // work items of half the output channels (item_of): two accumulator stages of C_out / 2 columns
+      p.CB = c.Cout / 2, p.nb = 1, p.acc_stages = 2, p.nsplit = 2;
+    } else {
+      p.CB = c.Cout / 2, p.nb = 2, p.acc_stages = 1;
+    }
   }
-  static const int cta2_env = getenv("SDAB_UMMA_CTA2") ? atoi(getenv("SDAB_UMMA_CTA2")) : 1;
-  const bool cta2 = cta2_env != 0 && c.Cout % 32 == 0;  // each CTA holds C_out / 2 weight rows (multiple of 16)
-  p.b_plane_bytes = (uint32_t)round_up((cta2 ? c.Cout / 2 : c.Cout) * 64, 1024);
+  p.b_plane_bytes = (uint32_t)round_up((cta2 ? c.Cout / 2 : c.Cout) / p.nsplit * 64, 1024);
   p.stage_bytes = p.planes * (kABytes + p.b_plane_bytes);
   p.staged = c.Cout % 32 == 0;
   p.out_chunks = c.Cout / 32;
+  p.item_chunks = p.out_chunks / p.nsplit;
   SDAB_REQUIRE(!(c.epi.outF && c.epi.pre), "a convolution writes either its output or its pre-activation, not both");
   SDAB_REQUIRE(!c.epi.ln || p.staged, "the fused LayerNorm epilogue needs C_out % 32 == 0");
   SDAB_REQUIRE(c.epi.ln != 2 || (c.epi.ln_a && c.epi.ln_rstd_in && !c.epi.bias && !c.epi.act && !c.epi.dact),
@@ -1340,14 +1382,12 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   SDAB_REQUIRE(p.sbufs >= 1 && p.sbufs <= 3, "staging sets out of range");
   // Patch kernel: plain stride-1 3x3 convolutions (the 36 block convolutions and their input-gradients)
   // on images that tile into 8 x 16 boxes; everything else keeps one TMA box per tap.
-  static const int patch_env = getenv("SDAB_UMMA_PATCH") ? atoi(getenv("SDAB_UMMA_PATCH")) : 1;
   static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
   static const int csplit_env = getenv("SDAB_UMMA_CSPLIT") ? atoi(getenv("SDAB_UMMA_CSPLIT")) : 0;
   p.csplit = csplit_env;
   SDAB_REQUIRE(c.epi.ln != 1 || (!c.epi.act && !c.epi.dact && !c.epi.pre),
                "the fused forward LayerNorm follows a plain (bias / residual) convolution");
-  p.patch = patch_env && cta2 && p.staged && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 && p.os == 1 &&
-            c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
+  p.patch = patch_ok;
   if (p.patch) {
     p.g.BW = kPatchBW, p.g.BH = kPatchBH, p.g.BN = 1;
     p.g.tiles_w = c.W / kPatchBW, p.g.tiles_h = c.H / kPatchBH, p.g.tiles_n = c.N;
@@ -1458,7 +1498,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   const Kernel kernel =
       p.patch ? patch_kernels[p.planes - 1][p.nb - 1][c.epi.ln] : kernels[p.planes - 1][p.nb - 1][c.epi.ln][cta2 ? 1 : 0];
   if (cta2) {
-    const int pairs = (p.g.num_tiles + 1) / 2;
+    const int pairs = (p.g.num_tiles + 1) / 2 * p.nsplit;  // pair-items
     const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(p.patch && patch_wg == 2 ? kPatchThreads : kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
