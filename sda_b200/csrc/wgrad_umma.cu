@@ -414,7 +414,9 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   p.ntg = (p.ntl + p.tg - 1) / p.tg;
   p.nmb = (p.nchunk_x + 3) / 4;
   p.nnb = c.Cg / p.nblk;
-  p.x_plane_bytes = 4 * kPatchSlot;
+  // (M = 128 always reads four chunk slots; with fewer input chunks the missing slots alias the next region of the
+  // stage -- rows whose results are never read -- and the stage shrinks enough for a third pipeline stage at C = 96)
+  p.x_plane_bytes = (uint32_t)(p.nchunk_x < 4 ? p.nchunk_x : 4) * kPatchSlot;
   p.g_plane_bytes = (uint32_t)(p.nblk / 32) * kGBytes;
   p.stage_bytes = p.planes * (p.x_plane_bytes + p.g_plane_bytes);
   p.stages = (int)((kSmemBudget - 2048) / p.stage_bytes);
