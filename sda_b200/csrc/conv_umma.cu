@@ -76,6 +76,7 @@ struct UmmaParams {
   int item_chunks; // 32-channel blocks of one work item (out_chunks / nsplit)
   int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
   uint32_t ctrl_bytes;  // control block in front of the staging tiles (barriers, TMEM slot, csplit statistics exchange)
+  int evict;       // epilogue TMA stores carry an L2 evict-first hint (SDAB_UMMA_EVICT, A/B switch)
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
@@ -249,6 +250,24 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                                              int c4) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+// The same with an L2 eviction-priority hint.  The epilogue outputs are read by the NEXT kernel, gigabytes later:
+// marked evict-first they stop displacing what this kernel re-reads (weights, patch halos, prefetched operands).
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4,
+                                                  uint64_t pol) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -495,10 +514,19 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
           // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
           // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
-          if (wantF) tma_store_3d(&tmF, staging, gc * 32, w0, n0 * p.H + h0);
-          if (wantO) {
-            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, gc, n0);
-            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0);
+          if (p.evict) {
+            const uint64_t pol = l2_evict_first_policy();
+            if (wantF) tma_store_3d_hint(&tmF, staging, gc * 32, w0, n0 * p.H + h0, pol);
+            if (wantO) {
+              tma_store_5d_hint(&tmO, staging + kStageF, 0, w0, h0, gc, n0, pol);
+              tma_store_5d_hint(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0, pol);
+            }
+          } else {
+            if (wantF) tma_store_3d(&tmF, staging, gc * 32, w0, n0 * p.H + h0);
+            if (wantO) {
+              tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, gc, n0);
+              tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0);
+            }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -646,10 +674,19 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       EPI_BARRIER();
       if (threadIdx.x == issuer) {
-        if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
-        if (wantO) {
-          tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
-          tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0);
+        if (p.evict) {
+          const uint64_t pol = l2_evict_first_policy();
+          if (wantF) tma_store_3d_hint(&tmF, staging, cc * 32, w0, n0 * p.H + h0, pol);
+          if (wantO) {
+            tma_store_5d_hint(&tmO, staging + kStageF, 0, w0, h0, cc, n0, pol);
+            tma_store_5d_hint(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0, pol);
+          }
+        } else {
+          if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
+          if (wantO) {
+            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
+            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0);
+          }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -1385,6 +1422,8 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
   static const int csplit_env = getenv("SDAB_UMMA_CSPLIT") ? atoi(getenv("SDAB_UMMA_CSPLIT")) : 0;
   p.csplit = csplit_env;
+  static const int evict_env = getenv("SDAB_UMMA_EVICT") ? atoi(getenv("SDAB_UMMA_EVICT")) : 0;
+  p.evict = evict_env;
   SDAB_REQUIRE(c.epi.ln != 1 || (!c.epi.act && !c.epi.dact && !c.epi.pre),
                "the fused forward LayerNorm follows a plain (bias / residual) convolution");
   p.patch = patch_ok;
