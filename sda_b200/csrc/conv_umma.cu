@@ -546,6 +546,30 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
   if (p.staged && threadIdx.x == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
+// The hi / lo words of 32 channels as loaded: converting them (load32_hilo) right after the request makes the
+// thread wait for the data on the spot, so a request issued ahead of its use must stay raw until then.
+struct RawHiLo {
+  uint4 h[4], l[4];
+};
+__device__ __forceinline__ void load_raw_hilo(const bf16* __restrict__ hi, const bf16* __restrict__ lo, RawHiLo& r) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r.h[j] = *reinterpret_cast<const uint4*>(hi + 8 * j);
+    r.l[j] = *reinterpret_cast<const uint4*>(lo + 8 * j);
+  }
+}
+__device__ __forceinline__ void convert_hilo(const RawHiLo& r, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t aw[4] = {r.h[j].x, r.h[j].y, r.h[j].z, r.h[j].w}, bw[4] = {r.l[j].x, r.l[j].y, r.l[j].z, r.l[j].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[8 * j + 2 * k] = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
+      o[8 * j + 2 * k + 1] = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ LayerNorm epilogue
 // Epilogue with the channel LayerNorm fused in (ConvEpilogue::ln: 1 forward, 2 adjoint), second generation.
 // The thread that owns a TMEM lane sees all C_out channels of its pixel, but not at once: the statistics need
@@ -720,40 +744,50 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
                             : p.epi.ln_nt > 1 ? p.epi.ln_shift + (size_t)(valid ? n : 0) * p.epi.ln_shift_stride
                                               : cst + kCstShift;
       const float* biasp = p.epi.bias ? cst : nullptr;
-      float rr[32];
-      if (has_res) load32(resp + cc0 * 32, rr);
+      // two residual blocks are in flight: blocks 0 and 1 are requested before the accumulator is waited for,
+      // block c + 2 once block c is consumed
+      float rr[2][32];
+      if (has_res) {
+        load32(resp + cc0 * 32, rr[0]);
+        if (cc0 + ccstep < nch) load32(resp + (cc0 + ccstep) * 32, rr[1]);
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       // ---- first sweep: f = acc + bias + res back into TMEM; shifted one-pass statistics of f + shift
       float s1 = 0.f, s2 = 0.f, K = 0.f;
-      for (int cc = cc0; cc < nch; cc += ccstep) {
-        float f[32];
-        tmem_ld32(t0 + cc * 32, f);
-        if (biasp) {
+      for (int cb = cc0; cb < nch; cb += 2 * ccstep) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(biasp + cc * 32 + j);
-            f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+        for (int u = 0; u < 2; ++u) {
+          const int cc = cb + u * ccstep;
+          if (cc < nch) {
+            float f[32];
+            tmem_ld32(t0 + cc * 32, f);
+            if (biasp) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(biasp + cc * 32 + j);
+                f[j] += b.x, f[j + 1] += b.y, f[j + 2] += b.z, f[j + 3] += b.w;
+              }
+            }
+            if (has_res) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += rr[u][j];
+              if (cc + 2 * ccstep < nch) load32(resp + (cc + 2 * ccstep) * 32, rr[u]);
+            }
+            tmem_st32(t0 + cc * 32, f);
+            if (cc == cc0) K = f[0] + (shiftp ? shiftp[cc * 32] : 0.f);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (shiftp) sh = *reinterpret_cast<const float4*>(shiftp + cc * 32 + j);
+              const float d0 = f[j] + sh.x - K, d1 = f[j + 1] + sh.y - K, d2 = f[j + 2] + sh.z - K,
+                          d3 = f[j + 3] + sh.w - K;
+              s1 += d0, s2 += d0 * d0;
+              s1 += d1, s2 += d1 * d1;
+              s1 += d2, s2 += d2 * d2;
+              s1 += d3, s2 += d3 * d3;
+            }
           }
-        }
-        if (has_res) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] += rr[j];
-          // consumed: request the next block's residual, it arrives while this block is finished
-          if (cc + ccstep < nch) load32(resp + (cc + ccstep) * 32, rr);
-        }
-        tmem_st32(t0 + cc * 32, f);
-        if (cc == cc0) K = f[0] + (shiftp ? shiftp[cc * 32] : 0.f);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (shiftp) sh = *reinterpret_cast<const float4*>(shiftp + cc * 32 + j);
-          const float d0 = f[j] + sh.x - K, d1 = f[j + 1] + sh.y - K, d2 = f[j + 2] + sh.z - K,
-                      d3 = f[j + 3] + sh.w - K;
-          s1 += d0, s2 += d0 * d0;
-          s1 += d1, s2 += d1 * d1;
-          s1 += d2, s2 += d2 * d2;
-          s1 += d3, s2 += d3 * d3;
         }
       }
       float mean, m2;
@@ -790,16 +824,22 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       }
     } else {
       // ---- adjoint: gx = res + (g - mean_C g - a sum_C(g a) / (C - 1)) rstd
-      float aa[32];
-      if (valid) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
+      // a: the next block is requested (raw words) while the current one is used
+      RawHiLo raw;
+      if (valid) load_raw_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, raw);
       const float rstd = valid ? p.epi.ln_rstd_in[pix] : 1.f;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       float sg = 0.f, sga = 0.f;
       for (int cc = cc0; cc < nch; cc += ccstep) {
-        float g[32];
+        float g[32], aa[32];
         tmem_ld32(t0 + cc * 32, g);
         if (valid) {
+          convert_hilo(raw, aa);
+          if (cc + ccstep < nch) {
+            const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
+            load_raw_hilo(an, an + lo_off, raw);
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             sg += g[j];
@@ -807,12 +847,6 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           }
         }
         if (stash) tmem_st32(ts + cc * 32, aa);
-        // consumed: request the next block of a, it arrives during the next accumulator load (a second register
-        // buffer was tried: it spills under the 168-register cap of the 320-thread kernel)
-        if (valid && cc + ccstep < nch) {
-          const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
-          load32_hilo(an, an + lo_off, aa);
-        }
       }
       float rr[32];
       if (has_res) load32(resp + cc0 * 32, rr);
@@ -826,12 +860,18 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       prefetch_tile(tile + nwg * (int)gridDim.x);
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float g[32], a[32];
+        // (no free TMEM columns for the stash: a is read again; requesting it one block ahead as raw words on
+        // top of the residual block spills under the 168-register cap, so it is requested just ahead of the
+        // accumulator load)
         if (!stash && valid) {
           const bf16* ac = a_pix + (size_t)cc * bs;
-          load32_hilo(ac, ac + lo_off, a);
+          load_raw_hilo(ac, ac + lo_off, raw);
         }
         tmem_ld32(t0 + cc * 32, g);
-        if (stash) tmem_ld32(ts + cc * 32, a);
+        if (stash)
+          tmem_ld32(ts + cc * 32, a);
+        else if (valid)
+          convert_hilo(raw, a);
         if (cc + ccstep >= nch) release_acc();
         if (valid) {
 #pragma unroll
