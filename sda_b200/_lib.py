@@ -115,7 +115,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     elif not LIB_PATH.exists():
         raise RuntimeError(f'{LIB_PATH} is missing: run `python -m sda_b200.build` (there is no CPU fallback)')
 
-    lib = ctypes.CDLL(str(LIB_PATH))
+    # SDAB_LIB: developer A/B switch (another build of the SAME ABI, e.g. sda_b200/build/libsdab_alt.so)
+    lib = ctypes.CDLL(os.environ.get('SDAB_LIB') or str(LIB_PATH))
 
     for name, (restype, argtypes) in _PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the ABI and the binding diverge

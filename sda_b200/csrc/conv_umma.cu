@@ -76,7 +76,6 @@ struct UmmaParams {
   int item_chunks; // 32-channel blocks of one work item (out_chunks / nsplit)
   int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
   uint32_t ctrl_bytes;  // control block in front of the staging tiles (barriers, TMEM slot, csplit statistics exchange)
-  int evict;       // epilogue TMA stores carry an L2 evict-first hint (SDAB_UMMA_EVICT, A/B switch)
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
 };
@@ -250,24 +249,6 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t sr
                                              int c4) {
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map),
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-               : "memory");
-}
-// The same with an L2 eviction-priority hint.  The epilogue outputs are read by the NEXT kernel, gigabytes later:
-// marked evict-first they stop displacing what this kernel re-reads (weights, patch halos, prefetched operands).
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ void tma_store_3d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, uint64_t pol) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ void tma_store_5d_hint(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4,
-                                                  uint64_t pol) {
-  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(map),
-               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -514,19 +495,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
           // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
           // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
-          if (p.evict) {
-            const uint64_t pol = l2_evict_first_policy();
-            if (wantF) tma_store_3d_hint(&tmF, staging, gc * 32, w0, n0 * p.H + h0, pol);
-            if (wantO) {
-              tma_store_5d_hint(&tmO, staging + kStageF, 0, w0, h0, gc, n0, pol);
-              tma_store_5d_hint(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0, pol);
-            }
-          } else {
-            if (wantF) tma_store_3d(&tmF, staging, gc * 32, w0, n0 * p.H + h0);
-            if (wantO) {
-              tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, gc, n0);
-              tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0);
-            }
+          if (wantF) tma_store_3d(&tmF, staging, gc * 32, w0, n0 * p.H + h0);
+          if (wantO) {
+            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, gc, n0);
+            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, p.out_chunks + gc, n0);
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
@@ -544,30 +516,6 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
     }
   }
   if (p.staged && threadIdx.x == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-}
-
-// The hi / lo words of 32 channels as loaded: converting them (load32_hilo) right after the request makes the
-// thread wait for the data on the spot, so a request issued ahead of its use must stay raw until then.
-struct RawHiLo {
-  uint4 h[4], l[4];
-};
-__device__ __forceinline__ void load_raw_hilo(const bf16* __restrict__ hi, const bf16* __restrict__ lo, RawHiLo& r) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    r.h[j] = *reinterpret_cast<const uint4*>(hi + 8 * j);
-    r.l[j] = *reinterpret_cast<const uint4*>(lo + 8 * j);
-  }
-}
-__device__ __forceinline__ void convert_hilo(const RawHiLo& r, float (&o)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t aw[4] = {r.h[j].x, r.h[j].y, r.h[j].z, r.h[j].w}, bw[4] = {r.l[j].x, r.l[j].y, r.l[j].z, r.l[j].w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      o[8 * j + 2 * k] = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
-      o[8 * j + 2 * k + 1] = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm epilogue
@@ -698,19 +646,10 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       EPI_BARRIER();
       if (threadIdx.x == issuer) {
-        if (p.evict) {
-          const uint64_t pol = l2_evict_first_policy();
-          if (wantF) tma_store_3d_hint(&tmF, staging, cc * 32, w0, n0 * p.H + h0, pol);
-          if (wantO) {
-            tma_store_5d_hint(&tmO, staging + kStageF, 0, w0, h0, cc, n0, pol);
-            tma_store_5d_hint(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0, pol);
-          }
-        } else {
-          if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
-          if (wantO) {
-            tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
-            tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0);
-          }
+        if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
+        if (wantO) {
+          tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
+          tma_store_5d(&tmO, staging + kStageF + kStageO, 0, w0, h0, nch + cc, n0);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
@@ -824,22 +763,16 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       }
     } else {
       // ---- adjoint: gx = res + (g - mean_C g - a sum_C(g a) / (C - 1)) rstd
-      // a: the next block is requested (raw words) while the current one is used
-      RawHiLo raw;
-      if (valid) load_raw_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, raw);
+      float aa[32];
+      if (valid) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
       const float rstd = valid ? p.epi.ln_rstd_in[pix] : 1.f;
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
       float sg = 0.f, sga = 0.f;
       for (int cc = cc0; cc < nch; cc += ccstep) {
-        float g[32], aa[32];
+        float g[32];
         tmem_ld32(t0 + cc * 32, g);
         if (valid) {
-          convert_hilo(raw, aa);
-          if (cc + ccstep < nch) {
-            const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
-            load_raw_hilo(an, an + lo_off, raw);
-          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             sg += g[j];
@@ -847,6 +780,14 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           }
         }
         if (stash) tmem_st32(ts + cc * 32, aa);
+        // consumed: request the next block of a, it arrives during the next accumulator load.  (Measured: a second
+        // register buffer, or keeping the request as raw words to convert at use, spills under the 168-register cap
+        // of the 320-thread kernel -- with ~28 KB of L1 left beside the shared memory the spill traffic goes to L2
+        // and the launch gets 30 % SLOWER.)
+        if (valid && cc + ccstep < nch) {
+          const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
+          load32_hilo(an, an + lo_off, aa);
+        }
       }
       float rr[32];
       if (has_res) load32(resp + cc0 * 32, rr);
@@ -860,18 +801,12 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       prefetch_tile(tile + nwg * (int)gridDim.x);
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float g[32], a[32];
-        // (no free TMEM columns for the stash: a is read again; requesting it one block ahead as raw words on
-        // top of the residual block spills under the 168-register cap, so it is requested just ahead of the
-        // accumulator load)
         if (!stash && valid) {
           const bf16* ac = a_pix + (size_t)cc * bs;
-          load_raw_hilo(ac, ac + lo_off, raw);
+          load32_hilo(ac, ac + lo_off, a);
         }
         tmem_ld32(t0 + cc * 32, g);
-        if (stash)
-          tmem_ld32(ts + cc * 32, a);
-        else if (valid)
-          convert_hilo(raw, a);
+        if (stash) tmem_ld32(ts + cc * 32, a);
         if (cc + ccstep >= nch) release_acc();
         if (valid) {
 #pragma unroll
@@ -1462,8 +1397,6 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
   static const int csplit_env = getenv("SDAB_UMMA_CSPLIT") ? atoi(getenv("SDAB_UMMA_CSPLIT")) : 0;
   p.csplit = csplit_env;
-  static const int evict_env = getenv("SDAB_UMMA_EVICT") ? atoi(getenv("SDAB_UMMA_EVICT")) : 0;
-  p.evict = evict_env;
   SDAB_REQUIRE(c.epi.ln != 1 || (!c.epi.act && !c.epi.dact && !c.epi.pre),
                "the fused forward LayerNorm follows a plain (bias / residual) convolution");
   p.patch = patch_ok;
