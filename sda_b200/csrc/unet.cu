@@ -81,7 +81,7 @@ struct Plan {
 };
 
 // one wave of at most ~150 CTAs, each leaving 512 TMEM columns x 128 lanes of fp32 partial sums
-constexpr size_t kWgradPartialBytes = (size_t)160 * 512 * 128 * sizeof(float);
+constexpr size_t kWgradPartialBytes = (size_t)300 * 512 * 128 * sizeof(float);
 
 size_t f_bytes(int N, int H, int W, int C) { return (size_t)N * H * W * C * sizeof(float); }
 size_t op_bytes(int N, int H, int W, int C) { return OpShape{N, H, W, C, 0}.bytes(); }

@@ -283,31 +283,49 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // dw[co][ci][tap] += sum over the pixel splits (fixed order: deterministic) of the partial sums the CTAs of one
-// wgrad_umma_kernel launch left behind, for every weight tap the tap-list entry feeds.  One thread per
-// (entry, ci, co), co fastest: the partial reads are coalesced; four independent accumulators keep loads in flight.
-__global__ void wgrad_reduce_kernel(const WParams p) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.ntl * p.cin * p.cout) return;
-  const int co = idx % p.cout, ci = (idx / p.cout) % p.cin, e = idx / (p.cout * p.cin);
-  const int mb = ci >> 7, nb = co / p.nblk;
-  const int tgi = e / p.tg, t = e - tgi * p.tg;
-  const size_t stride = (size_t)p.tg * 128 * p.nblk;
-  const float* src = p.part + (((size_t)(tgi * p.nmb + mb) * p.nnb + nb) * p.splits * p.tg + t) * 128 * p.nblk +
-                     (size_t)(ci & 127) * p.nblk + (co - nb * p.nblk);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int sp = 0;
-  for (; sp + 4 <= p.splits; sp += 4) {
-    s0 += src[(size_t)sp * stride], s1 += src[(size_t)(sp + 1) * stride];
-    s2 += src[(size_t)(sp + 2) * stride], s3 += src[(size_t)(sp + 3) * stride];
+// wgrad_umma_kernel launch left behind, for every weight tap the tap-list entry feeds.
+// A block owns 32 output x 2 input channels and ALL entries of the tap list, one thread per (entry, ci, co): it sums
+// the splits of its element (partials are read along co: full lines; thousands of threads keep the L2 latency
+// covered even at 74 splits) and drops the sum into a shared-memory image of the block's piece of dw, which then
+// leaves as rows of 2 x 9 = 18 consecutive floats per output channel.  (First version: each thread added straight
+// into dw -- adjacent lanes were cin x 9 floats apart, one 32-byte sector per atomic: 60 us per launch, more than
+// half of the main kernel's time.)
+constexpr int kRedCo = 32, kRedCi = 2, kRedRow = kRedCi * 9 + 1;
+__global__ void __launch_bounds__(kRedCo * kRedCi * 9) wgrad_reduce_kernel(const WParams p) {
+  __shared__ float out[kRedCo * kRedRow];
+  const int col = threadIdx.x % kRedCo, cil = threadIdx.x / kRedCo % kRedCi, e = threadIdx.x / (kRedCo * kRedCi);
+  const int ci0 = blockIdx.x * kRedCi, co0 = blockIdx.y * kRedCo;
+  const int ci = ci0 + cil, co = co0 + col;
+  for (int i = threadIdx.x; i < kRedCo * kRedRow; i += blockDim.x) out[i] = 0.f;
+  __syncthreads();
+  if (ci < p.cin && co < p.cout) {
+    const int mb = ci >> 7, nb = co / p.nblk;
+    const size_t stride = (size_t)p.tg * 128 * p.nblk;
+    const int tgi = e / p.tg, t = e - tgi * p.tg;
+    const float* src = p.part + (((size_t)(tgi * p.nmb + mb) * p.nnb + nb) * p.splits * p.tg + t) * 128 * p.nblk +
+                       (size_t)(ci & 127) * p.nblk + (co - nb * p.nblk);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int sp = 0;
+    for (; sp + 4 <= p.splits; sp += 4) {
+      s0 += src[(size_t)sp * stride], s1 += src[(size_t)(sp + 1) * stride];
+      s2 += src[(size_t)(sp + 2) * stride], s3 += src[(size_t)(sp + 3) * stride];
+    }
+    for (; sp < p.splits; ++sp) s0 += src[(size_t)sp * stride];
+    const float sum = (s0 + s1) + (s2 + s3);
+    const uint32_t mask = p.tl_mask[e];
+    // the taps of different entries are disjoint in every tap list unet.cu builds (one addend per element, so the
+    // result is deterministic); the shared-memory atomics keep overlapping masks correct too
+    float* mine = out + col * kRedRow + cil * 9;
+    for (int tap = 0; tap < 9; ++tap)
+      if (mask >> tap & 1u) atomicAdd(mine + tap, sum);
   }
-  for (; sp < p.splits; ++sp) s0 += src[(size_t)sp * stride];
-  const float sum = (s0 + s1) + (s2 + s3);
-  const uint32_t mask = p.tl_mask[e];
-  float* dst = p.dw + ((size_t)co * p.cin + ci) * 9;
-  // the taps of different entries are disjoint in every tap list unet.cu builds; atomics keep overlapping
-  // masks correct too (one addend per element and launch otherwise, so the result stays deterministic)
-  for (int tap = 0; tap < 9; ++tap)
-    if (mask >> tap & 1u) atomicAdd(dst + tap, sum);
+  __syncthreads();
+  // one thread per element and launch, launches are stream-ordered: a plain read-modify-write is exact
+  const int nci = min(kRedCi, p.cin - ci0);
+  for (int idx = threadIdx.x; idx < kRedCo * kRedCi * 9; idx += blockDim.x) {
+    const int r = idx / (kRedCi * 9), k = idx - r * (kRedCi * 9);
+    if (co0 + r < p.cout && k < nci * 9) p.dw[((size_t)(co0 + r) * p.cin + ci0) * 9 + k] += out[r * kRedRow + k];
+  }
 }
 
 // db[c] += sum over the interior pixels of an operand tensor (hi + lo).  grid: (row groups, C / 32); block: 256
@@ -409,9 +427,11 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   }
   p.x_par = c.x_par, p.g_par = c.g_par, p.g_dh = c.g_dh, p.g_dw = c.g_dw;
   SDAB_REQUIRE(p.x_par >= 0 && p.x_par <= 4 && p.g_par >= 0 && p.g_par <= 4, "invalid parity image");
-  p.tg = 512 / p.nblk;
-  if (p.tg > p.ntl) p.tg = p.ntl;
-  p.ntg = (p.ntl + p.tg - 1) / p.tg;
+  // taps per CTA: as many as fit the 512 TMEM columns, evened out over the tap groups (nine taps at nblk = 128 are
+  // 3 + 3 + 3, not 4 + 4 + 1: a launch lasts as long as its longest CTAs)
+  const int tg_max = 512 / p.nblk;
+  p.ntg = (p.ntl + tg_max - 1) / tg_max;
+  p.tg = (p.ntl + p.ntg - 1) / p.ntg;
   p.nmb = (p.nchunk_x + 3) / 4;
   p.nnb = c.Cg / p.nblk;
   // (M = 128 always reads four chunk slots; with fewer input chunks the missing slots alias the next region of the
@@ -419,14 +439,28 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   p.x_plane_bytes = (uint32_t)(p.nchunk_x < 4 ? p.nchunk_x : 4) * kPatchSlot;
   p.g_plane_bytes = (uint32_t)(p.nblk / 32) * kGBytes;
   p.stage_bytes = p.planes * (p.x_plane_bytes + p.g_plane_bytes);
-  p.stages = (int)((kSmemBudget - 2048) / p.stage_bytes);
+  // ... except behind the LAST plane of the last stage, where the phantom slots can stick out of the stage (one
+  // input chunk, single plane): the allocation carries that much slack, an MMA must not read past it
+  const long over = (long)(p.planes - 1) * p.x_plane_bytes + 4L * kPatchSlot - (long)p.stage_bytes;
+  const uint32_t slack = over > 0 ? (uint32_t)over : 0u;
+  p.stages = (int)((kSmemBudget - 2048 - slack) / p.stage_bytes);
   if (p.stages > 3) p.stages = 3;
   SDAB_REQUIRE(p.stages >= 1, "weight-gradient tile does not fit shared memory");
   const int units = p.ntg * p.nmb * p.nnb;
-  // one wave of CTAs: every extra pixel split repeats the epilogue's atomics over the whole gradient
-  static const int waves_x2 = getenv("SDAB_WGRAD_WAVES_X2") ? atoi(getenv("SDAB_WGRAD_WAVES_X2")) : 2;
-  p.splits = (waves_x2 * 74 + units - 1) / units;
-  if (p.splits > p.num_tiles) p.splits = p.num_tiles;
+  // Pixel splits: CTAs run one per SM (each allocates all 512 TMEM columns), so a launch lasts
+  // waves x tiles-per-CTA = ceil(units s / 148) x ceil(num_tiles / s) tile periods; the split count minimises that
+  // (smallest s on ties: every split adds a pass over the gradient to the reduction).  (The first version took
+  // ceil(148 / units): 162 CTAs at units = 27, i.e. a second wave for 14 of them -- 2 x 1/6 instead of 1 x 1/5.)
+  static const int wg_sms = getenv("SDAB_WGRAD_SMS") ? atoi(getenv("SDAB_WGRAD_SMS")) : 148;
+  {
+    long best = -1;
+    const int smax = p.num_tiles < 2 * wg_sms ? p.num_tiles : 2 * wg_sms;
+    for (int s = 1; s <= smax; ++s) {
+      if (c.partial && (size_t)units * s * p.tg * 128 * p.nblk * sizeof(float) > c.partial_bytes) break;
+      const long cost = (long)((units * s + wg_sms - 1) / wg_sms) * ((p.num_tiles + s - 1) / s);
+      if (best < 0 || cost < best) best = cost, p.splits = s;
+    }
+  }
   p.cin = c.cin, p.cout = c.cout, p.dw = c.dw;
   // split partial sums in the caller's workspace when it is large enough, fp32 atomics otherwise
   const size_t part_bytes = (size_t)units * p.splits * p.tg * 128 * p.nblk * sizeof(float);
@@ -457,7 +491,7 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
   };
   SDAB_TRY(make_map(&tmX, c.xOP, p.nchunk_x, p.x_par, false, kPW, BH + 2));
   SDAB_TRY(make_map(&tmG, c.gOP, p.nchunk_g, p.g_par, true, kBW, BH));
-  const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes;
+  const size_t smem = 2048 + (size_t)p.stages * p.stage_bytes + slack;
   static bool attr_set = false;
   if (!attr_set) {
     SDAB_CUDA_CHECK(cudaFuncSetAttribute(wgrad_umma_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -471,7 +505,7 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
     wgrad_umma_kernel<1, 16><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
   SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
   if (p.part) {
-    wgrad_reduce_kernel<<<(p.ntl * p.cin * p.cout + 255) / 256, 256, 0, stream>>>(p);
+    wgrad_reduce_kernel<<<dim3((p.cin + kRedCi - 1) / kRedCi, (p.cout + kRedCo - 1) / kRedCo), kRedCo * kRedCi * p.ntl, 0, stream>>>(p);
     SDAB_LAUNCH_CHECK("wgrad_reduce_kernel");
   }
   if (c.db) {
