@@ -75,6 +75,8 @@ struct UmmaParams {
   int nsplit;      // patch kernel, C_out > 256 without LayerNorm: a work item is (tile, half of the output channels)
   int item_chunks; // 32-channel blocks of one work item (out_chunks / nsplit)
   int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
+  int pieces;      // patch kernel, C_out = 384 with a fused LayerNorm: the accumulator of a tile is built as `pieces`
+                   // consecutive N = CB items in a ring of acc_stages TMEM slots (1: one item per tile)
   uint32_t ctrl_bytes;  // control block in front of the staging tiles (barriers, TMEM slot, csplit statistics exchange)
   int debug;       // SDAB_UMMA_DEBUG bits (developer ablation): 1 = no MMA issue, 2 = no TMA, 4 = no epilogue work
   ConvEpilogue epi;
@@ -533,7 +535,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
 // Single accumulator (C_out > 256, patch kernel): the two epilogue warpgroups split the channel blocks of every
 // tile (csplit) and exchange their partial statistics through shared memory (xchg) -- both warpgroups of a
 // pixel combine the two partials in the same order, so they normalise with identical numbers.
-template <int LN, bool CTA2>
+template <int LN, bool CTA2, int PC = 1>
 __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
                                                  uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
                                                  uint32_t acc_stride, uint32_t staging_base, const float* cst,
@@ -553,12 +555,38 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
   const OpShape so{0, p.Ho, p.Wo, C, 0};
   const size_t bs = so.block_stride(), lo_off = so.lo_offset();
   const float invC = 1.f / (float)C, invC1 = 1.f / (float)(C - 1);
-  const bool stash = LN == 2 && (p.acc_stages == 2 ? C <= 128 : C <= 256);
+  // PC > 1: the accumulator of a tile arrives as PC pieces of 128 columns (4 channel blocks) in a ring of 4 TMEM
+  // slots (compile-time geometry: the slot arithmetic must not cost the other variants instructions or registers)
+  const bool stash = LN == 2 && PC == 1 && (p.acc_stages == 2 ? C <= 128 : C <= 256);
   int it = wg;
   int sbuf = 0;
   for (int tile = tile_begin + wg * (int)gridDim.x; tile < tile_end; tile += nwg * (int)gridDim.x, it += nwg) {
-    const int acc = it % p.acc_stages;
-    const uint32_t acc_phase = (it / p.acc_stages) & 1;
+    // Piece j of this tile is accumulator item it * npc + j: TMEM slot and barrier phase follow from that index.
+    // The pieces are waited for as the first sweep reaches them and handed back as the second sweep leaves them,
+    // so the MMAs of the next tile's pieces run under this tile's epilogue (4 slots of 128 columns hold the 3
+    // pieces of a C_out = 384 tile plus the first piece of the next one).
+    const int itb = PC == 1 ? it : it * PC;
+    auto acc_of = [&](int j) { return PC == 1 ? itb % p.acc_stages : (itb + j) & 3; };
+    auto phase_of = [&](int j) { return (uint32_t)(PC == 1 ? (itb / p.acc_stages) & 1 : ((itb + j) >> 2) & 1); };
+    int ready = -1;
+    auto wait_first = [&]() {  // one accumulator per tile: waited for once, ahead of the first sweep
+      if constexpr (PC == 1) {
+        mbar_wait(bar_tfull + 8 * acc_of(0), phase_of(0));
+        tc_fence_after();
+      }
+    };
+    auto wait_block = [&](int cc) {  // pieces: waited for as the first sweep reaches them
+      if constexpr (PC > 1) {
+        const int j = cc >> 2;
+        if (j > ready) {
+          while (ready < j) {
+            ++ready;
+            mbar_wait(bar_tfull + 8 * acc_of(ready), phase_of(ready));
+          }
+          tc_fence_after();
+        }
+      }
+    };
     int n0, h0, w0;
     p.g.tile_origin(tile, n0, h0, w0);
     const int n = n0 + bn, h = p.os * (h0 + bh) + p.oh0, w = p.os * (w0 + bw) + p.ow0;
@@ -568,8 +596,13 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
     const bool has_res = p.epi.res != nullptr && valid;
     const float* resp = p.epi.res + pix * C;
     const bf16* a_pix = (LN == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
-    const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
-    const uint32_t ts = t0 + (uint32_t)C;  // stash columns (adjoint)
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t t0 = tq + (uint32_t)acc_of(0) * acc_stride;
+    auto col_of = [&](int cc) {  // TMEM address of channel block cc of this tile
+      if constexpr (PC == 1) return t0 + (uint32_t)cc * 32u;
+      return tq + (uint32_t)acc_of(cc >> 2) * 128u + (uint32_t)(cc & 3) * 32u;
+    };
+    const uint32_t ts = t0 + (uint32_t)C;  // stash columns (adjoint, PC == 1)
     // Pulls the epilogue operands of this thread's pixel of tile `pt` into L2.  Called for the NEXT tile of this
     // warpgroup between the two sweeps of the current one (and for the very first tile at its start): at the
     // 5 TB/s these kernels stream, L2 holds some 25 us of traffic, so a request issued a whole tile period
@@ -655,15 +688,17 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       }
       if (++sbuf == p.sbufs) sbuf = 0;
     };
-    // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
-    auto release_acc = [&]() {
+    // block cc was this warpgroup's last TMEM read of its piece: hand the piece's slot back to the MMA warp
+    auto release_after = [&](int cc) {
+      const int j = PC == 1 ? 0 : cc >> 2;
+      if (cc + ccstep < nch && (PC == 1 || (cc + ccstep) >> 2 == j)) return;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if constexpr (CTA2)
-          mbar_arrive_leader(bar_tempty + 8 * acc);
+          mbar_arrive_leader(bar_tempty + 8 * acc_of(j));
         else
-          mbar_arrive(bar_tempty + 8 * acc);
+          mbar_arrive(bar_tempty + 8 * acc_of(j));
       }
     };
     // partial statistics of the two warpgroups of a csplit tile -> both partials, in warpgroup order
@@ -690,8 +725,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
         load32(resp + cc0 * 32, rr[0]);
         if (cc0 + ccstep < nch) load32(resp + (cc0 + ccstep) * 32, rr[1]);
       }
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
+      wait_first();
       // ---- first sweep: f = acc + bias + res back into TMEM; shifted one-pass statistics of f + shift
       float s1 = 0.f, s2 = 0.f, K = 0.f;
       for (int cb = cc0; cb < nch; cb += 2 * ccstep) {
@@ -700,7 +734,8 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           const int cc = cb + u * ccstep;
           if (cc < nch) {
             float f[32];
-            tmem_ld32(t0 + cc * 32, f);
+            wait_block(cc);
+            tmem_ld32(col_of(cc), f);
             if (biasp) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -713,7 +748,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
               for (int j = 0; j < 32; ++j) f[j] += rr[u][j];
               if (cc + 2 * ccstep < nch) load32(resp + (cc + 2 * ccstep) * 32, rr[u]);
             }
-            tmem_st32(t0 + cc * 32, f);
+            tmem_st32(col_of(cc), f);
             if (cc == cc0) K = f[0] + (shiftp ? shiftp[cc * 32] : 0.f);
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -749,8 +784,8 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       // ---- second sweep: F <- f, OP <- (f + shift - mean) rstd
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float f[32];
-        tmem_ld32(t0 + cc * 32, f);
-        if (cc + ccstep >= nch) release_acc();
+        tmem_ld32(col_of(cc), f);
+        release_after(cc);
         stage_and_store(cc, f, [&](float (&v)[32]) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -766,12 +801,12 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       float aa[32];
       if (valid) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
       const float rstd = valid ? p.epi.ln_rstd_in[pix] : 1.f;
-      mbar_wait(bar_tfull + 8 * acc, acc_phase);
-      tc_fence_after();
+      wait_first();
       float sg = 0.f, sga = 0.f;
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float g[32];
-        tmem_ld32(t0 + cc * 32, g);
+        wait_block(cc);
+        tmem_ld32(col_of(cc), g);
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -805,9 +840,9 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           const bf16* ac = a_pix + (size_t)cc * bs;
           load32_hilo(ac, ac + lo_off, a);
         }
-        tmem_ld32(t0 + cc * 32, g);
+        tmem_ld32(col_of(cc), g);
         if (stash) tmem_ld32(ts + cc * 32, a);
-        if (cc + ccstep >= nch) release_acc();
+        release_after(cc);
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) g[j] = (g[j] - mg - a[j] * beta) * rstd + (has_res ? rr[j] : 0.f);
@@ -1059,7 +1094,7 @@ __device__ __forceinline__ uint64_t desc64_patch(uint32_t lo) { return ((uint64_
 // tap inner over TWO rings: the patch ring (a_stages x PLANES x 12 KB, one box per K-block) and the
 // weight ring (stages x one (tap, K-block) weight block).  Input traffic from L2 and into shared
 // memory drops from 9 x 8 KB to 11.25 KB per (plane, K-block).
-template <int PLANES, int NB, int LN, bool CTA2>
+template <int PLANES, int NB, int LN, bool CTA2, int PC = 1>
 __global__ void __launch_bounds__(kPatchThreads, 1)
     conv_umma_patch_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmB,
                            const __grid_constant__ CUtensorMap tmF, const __grid_constant__ CUtensorMap tmO,
@@ -1073,9 +1108,9 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const uint32_t bar_bempty = base + 128;     // kMaxBStages x 8 B
   const uint32_t bar_afull = base + 256;      // kMaxAStages x 8 B
   const uint32_t bar_aempty = base + 288;     // kMaxAStages x 8 B
-  const uint32_t bar_tfull = base + 320;      // 2 x 8 B
-  const uint32_t bar_tempty = base + 336;     // 2 x 8 B
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 352);
+  const uint32_t bar_tfull = base + 320;      // 4 x 8 B
+  const uint32_t bar_tempty = base + 352;     // 4 x 8 B
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + 384);
   const uint32_t staging0 = base + p.ctrl_bytes;
   const uint32_t aring0 = staging0 + 2 * p.sbufs * kStagingBytes;  // one staging set per epilogue warpgroup
   constexpr uint32_t a_stage_bytes = PLANES * kPatchPlane;
@@ -1089,7 +1124,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
   // single accumulator (C_out > 256): the two epilogue warpgroups split every tile's channel blocks (with a fused
   // LayerNorm they exchange their partial statistics, epilogue_ln_role)
-  const bool csplit = (p.acc_stages == 1 || (LN == 0 && p.csplit)) && blockDim.x == kPatchThreads;
+  const bool csplit = (p.acc_stages == 1 || PC > 1 || (LN == 0 && p.csplit)) && blockDim.x == kPatchThreads;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -1100,7 +1135,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, (CTA2 ? 8 : 4) * (csplit ? 2 : 1));  // one arrival per epilogue warp
     }
@@ -1109,11 +1144,11 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   }
   if (warp == 1) {
     if constexpr (CTA2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 352), "r"(512u)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 384), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 352), "r"(512u)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 384), "r"(512u)
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -1132,7 +1167,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const uint32_t acc_stride = p.acc_stages == 2 ? 256u : 0u;
+  const uint32_t acc_stride = p.acc_stages == 4 ? 128u : p.acc_stages == 2 ? 256u : 0u;
   const int cbh = CTA2 ? p.CB / 2 : p.CB;  // B rows of one N half held by this CTA
   // pair-items of this launch (item_of); for nsplit == 1 "(vt >> 1) < v_end" is "tile < tile_end"
   const int v_end = ((p.g.num_tiles + 1) >> 1) * p.nsplit;
@@ -1145,7 +1180,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     const uint32_t b_tx = (CTA2 ? 2u : 1u) * PLANES * (uint32_t)(NB * cbh) * 64u;
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
-    int a_vt = tile_begin, a_chunk = 0;  // cursor of the patch ring (virtual tile = work item, item_of)
+    int a_vt = tile_begin, a_piece = 0, a_chunk = 0;  // cursor of the patch ring (virtual tile = work item, item_of)
     auto issue_patch = [&]() {
       if ((a_vt >> 1) >= v_end) return;
       int a_tile, a_nh, n0, h0, w0;
@@ -1166,12 +1201,17 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
       }
       __syncwarp();
       if (++as == p.a_stages) as = 0, aph ^= 1;
-      if (++a_chunk == p.nchunk) a_chunk = 0, a_vt += gridDim.x;
+      // (every accumulator piece of a tile walks the K-blocks again: the patch is fetched once per piece)
+      if (++a_chunk == p.nchunk) {
+        a_chunk = 0;
+        if (++a_piece == PC) a_piece = 0, a_vt += gridDim.x;
+      }
     };
     issue_patch();
     for (int vt = tile_begin; (vt >> 1) < v_end; vt += gridDim.x) {
       int tile, nh;
       item_of(p, vt, tile, nh);
+      for (int piece = 0; piece < PC; ++piece)
       for (int chunk = 0; chunk < p.nchunk; ++chunk) {
         issue_patch();
         for (int tap = 0; tap < 9; ++tap) {
@@ -1186,7 +1226,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
 #pragma unroll
               for (int half = 0; half < NB; ++half) {
                 const uint32_t dst = sb + pl * p.b_plane_bytes + half * cbh * 64;
-                const int row = brow + pl * p.Cout + (nh + half) * p.CB + (CTA2 ? (int)rank * cbh : 0);
+                const int row = brow + pl * p.Cout + (nh + piece + half) * p.CB + (CTA2 ? (int)rank * cbh : 0);
                 if constexpr (CTA2)
                   tma_load_2d_2sm(dst, &tmB, full, 0, row);
                 else
@@ -1211,7 +1251,12 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     int as = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
     int it = 0;
-    for (int vt = tile_begin; leader && (vt >> 1) < v_end; vt += gridDim.x, ++it) {
+    for (int vi = 0, vt = tile_begin; leader && (vt >> 1) < v_end; ++vi, ++it) {
+      // (vi walks the accumulator items: `pieces` consecutive ones per tile)
+      if (vi == PC) {
+        vi = 0, vt += gridDim.x;
+        if ((vt >> 1) >= v_end) break;
+      }
       const int acc = it % p.acc_stages;
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
       mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -1267,10 +1312,10 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
     const int wg = (warp - 2) >> 2, nwg = ((p.acc_stages == 2 || csplit) && blockDim.x == kPatchThreads) ? 2 : 1;
     if (wg < nwg) {
       if constexpr (LN != 0)
-        epilogue_ln_role<LN, CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0,
-                                   reinterpret_cast<const float*>(base_ptr + kCtrlBytes),
-                                   reinterpret_cast<float2*>(base_ptr + kCtrlBytes + kCstBytes), tile_begin, tile_end,
-                                   warp, lane, wg, nwg, csplit);
+        epilogue_ln_role<LN, CTA2, PC>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0,
+                                       reinterpret_cast<const float*>(base_ptr + kCtrlBytes),
+                                       reinterpret_cast<float2*>(base_ptr + kCtrlBytes + kCstBytes), tile_begin, tile_end,
+                                       warp, lane, wg, nwg, csplit);
       else
         epilogue_role<CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
                             warp, lane, wg, nwg, csplit);
@@ -1367,8 +1412,14 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   static const int nsplit_env = getenv("SDAB_UMMA_NSPLIT") ? atoi(getenv("SDAB_UMMA_NSPLIT")) : 1;
   const bool patch_ok = patch_env && cta2 && c.Cout % 32 == 0 && c.stride == 1 && !p.in_s2 && !c.taps.n && wtaps == 9 &&
                         p.os == 1 && c.W % kPatchBW == 0 && c.H % kPatchBH == 0;
-  p.nsplit = 1;
-  if (c.Cout <= 256) {
+  p.nsplit = 1, p.pieces = 1;
+  static const int pieces_env = getenv("SDAB_UMMA_PIECES") ? atoi(getenv("SDAB_UMMA_PIECES")) : 1;
+  if (patch_ok && pieces_env && c.epi.ln && c.Cout == 384) {
+    // fused LayerNorm at C_out = 384: the statistics span all channels, so the tile stays one epilogue unit, but its
+    // accumulator is built as three N = 128 items in a ring of four TMEM slots -- the MMAs of the next tile's
+    // pieces run under this tile's epilogue (a single 384-column accumulator made them wait for it)
+    p.CB = 128, p.nb = 1, p.acc_stages = 4, p.pieces = 3;  // (kernel template argument PC = 3)
+  } else if (c.Cout <= 256) {
     p.CB = c.Cout, p.nb = 1, p.acc_stages = 2;
   } else {
     SDAB_REQUIRE(c.Cout % 32 == 0, "C_out above 256 must be a multiple of 32");
@@ -1379,7 +1430,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
       p.CB = c.Cout / 2, p.nb = 2, p.acc_stages = 1;
     }
   }
-  p.b_plane_bytes = (uint32_t)round_up((cta2 ? c.Cout / 2 : c.Cout) / p.nsplit * 64, 1024);
+  p.b_plane_bytes = (uint32_t)round_up((cta2 ? c.Cout / 2 : c.Cout) / (p.nsplit * p.pieces) * 64, 1024);
   p.stage_bytes = p.planes * (kABytes + p.b_plane_bytes);
   p.staged = c.Cout % 32 == 0;
   p.out_chunks = c.Cout / 32;
@@ -1406,7 +1457,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     p.g.num_tiles = p.g.tiles_w * p.g.tiles_h * p.g.tiles_n;
     p.b_stage_bytes = p.planes * p.b_plane_bytes;
     // csplit statistics exchange of the LayerNorm epilogue: 2 tile parities x 2 warpgroups x 128 pixels x float2
-    if (c.epi.ln && p.acc_stages == 1 && patch_wg == 2) p.ctrl_bytes += kXchgBytes;
+    if (c.epi.ln && (p.acc_stages == 1 || p.pieces > 1) && patch_wg == 2) p.ctrl_bytes += kXchgBytes;
     const uint32_t fixed = p.ctrl_bytes + 1024 + 2 * p.sbufs * kStagingBytes;
     p.a_stages = 3;
     p.stages = (int)((kSmemBudget - fixed - p.a_stages * p.planes * kPatchPlane) / p.b_stage_bytes);
@@ -1491,8 +1542,15 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
 #define SDAB_KP(P, B) {conv_umma_patch_kernel<P, B, 0, true>, conv_umma_patch_kernel<P, B, 1, true>, conv_umma_patch_kernel<P, B, 2, true>}
   static const Kernel patch_kernels[2][2][3] = {{SDAB_KP(1, 1), SDAB_KP(1, 2)}, {SDAB_KP(2, 1), SDAB_KP(2, 2)}};
 #undef SDAB_KP
+  // accumulator pieces (fused LayerNorm at C_out = 384): [planes - 1][ln - 1]
+  static const Kernel piece_kernels[2][2] = {
+      {conv_umma_patch_kernel<1, 1, 1, true, 3>, conv_umma_patch_kernel<1, 1, 2, true, 3>},
+      {conv_umma_patch_kernel<2, 1, 1, true, 3>, conv_umma_patch_kernel<2, 1, 2, true, 3>}};
   static bool attr_set = false;
   if (!attr_set) {
+    for (int a = 0; a < 2; ++a)
+      for (int l = 0; l < 2; ++l)
+        SDAB_CUDA_CHECK(cudaFuncSetAttribute(piece_kernels[a][l], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
         for (int l = 0; l < 3; ++l)
@@ -1507,8 +1565,9 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     attr_set = true;
   }
   SDAB_REQUIRE(c.epi.ln >= 0 && c.epi.ln <= 2, "unknown fused LayerNorm variant");
-  const Kernel kernel =
-      p.patch ? patch_kernels[p.planes - 1][p.nb - 1][c.epi.ln] : kernels[p.planes - 1][p.nb - 1][c.epi.ln][cta2 ? 1 : 0];
+  const Kernel kernel = p.pieces > 1 ? piece_kernels[p.planes - 1][c.epi.ln - 1]
+                        : p.patch    ? patch_kernels[p.planes - 1][p.nb - 1][c.epi.ln]
+                                     : kernels[p.planes - 1][p.nb - 1][c.epi.ln][cta2 ? 1 : 0];
   if (cta2) {
     const int pairs = (p.g.num_tiles + 1) / 2 * p.nsplit;  // pair-items
     const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
