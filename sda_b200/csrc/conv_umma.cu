@@ -30,6 +30,13 @@ namespace sdab {
 
 namespace {
 
+// Developer ablation of the patch kernel / LayerNorm epilogue, compiled in only by -DSDAB_ABLATE=bits (a separate
+// build for SDAB_LIB, wrong results by design): 1 no MMA issue, 16 no global epilogue operands, 32 no epilogue stores,
+// 64 staging written but no TMA store issued, 128 no F output (OP only)
+#ifndef SDAB_ABLATE
+#define SDAB_ABLATE 0
+#endif
+constexpr int kAblate = SDAB_ABLATE;
 constexpr int kThreads = 192;
 constexpr int kPatchThreads = 320;  // patch kernel: two epilogue warpgroups (warps 2-5 and 6-9)
 constexpr uint32_t kABytes = 128 * 64;  // one A box: 128 pixels x 32 channels x bf16
@@ -400,12 +407,13 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
       // Staged epilogue: every output leaves the SM as full cache lines.  Per 32-channel block the
       // 128 threads (one pixel each) write their values into swizzled staging tiles; one thread
       // then issues TMA stores (F: [pixels][C] matrix, OP: the (plane, K-block) image box).
-      const bool wantF = p.epi.outF != nullptr || p.epi.pre != nullptr;
+      const bool wantF = (p.epi.outF != nullptr || p.epi.pre != nullptr) && !(kAblate & 128);
       const bool wantO = p.epi.outOP != nullptr;
       const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
       const OpShape so{0, p.Ho, p.Wo, p.Cout, 0};
       // developer ablation bits: 16 = no global operand loads, 32 = no stores
-      const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16), has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16);
+      const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16) && !(kAblate & 16),
+                 has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16) && !(kAblate & 16);
       {
         // pull the next item's epilogue operands of this pixel row into L2 one item ahead
         const int nvt = vt + nwg * (int)gridDim.x;
@@ -442,7 +450,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           }
         }
         epilogue_math32(p.epi, v, f, rr, has_res, has_dact, gc * 32);
-        if (p.debug & 32) continue;
+        if ((p.debug & 32) || (kAblate & 32)) continue;
         // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
         const uint32_t staging = staging0 + sbuf * kStagingBytes;
         if (threadIdx.x == issuer) {
@@ -493,7 +501,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         EPI_BARRIER();
-        if (threadIdx.x == issuer && !(p.debug & 128)) {
+        if (threadIdx.x == issuer && !(p.debug & 128) && !(kAblate & 64)) {
           // asynchronous copy-out by the TMA engine: F as rows of the [pixels][C] matrix, OP as the
           // (plane, K-block) image box; up to `sbufs` blocks are in flight behind the epilogue
           // the tensor maps already carry the output placement (stride os, offset (oh0, ow0), halo)
@@ -551,7 +559,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
   const int m = q * 32 + lane;
   const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
   const int C = p.Cout, nch = p.out_chunks;
-  const bool wantF = p.epi.outF != nullptr, wantO = p.epi.outOP != nullptr;
+  const bool wantF = p.epi.outF != nullptr && !(kAblate & 128), wantO = p.epi.outOP != nullptr;
   const OpShape so{0, p.Ho, p.Wo, C, 0};
   const size_t bs = so.block_stride(), lo_off = so.lo_offset();
   const float invC = 1.f / (float)C, invC1 = 1.f / (float)(C - 1);
@@ -593,7 +601,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
     const bool valid = n < p.N;
     const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
     const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
-    const bool has_res = p.epi.res != nullptr && valid;
+    const bool has_res = p.epi.res != nullptr && valid && !(kAblate & 16);
     const float* resp = p.epi.res + pix * C;
     const bf16* a_pix = (LN == 2 && valid) ? p.epi.ln_a + op_offset(so, n, h + 1, w + 1) : nullptr;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -628,6 +636,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
 
     // output of one 32-channel block through the staging tiles: F <- v (fp32), then OP <- post(v) (bf16 hi / lo)
     auto stage_and_store = [&](int cc, float (&v)[32], auto&& post) {
+      if constexpr ((kAblate & 32) != 0) return;
       const uint32_t staging = staging0 + sbuf * kStagingBytes;
       if (threadIdx.x == issuer) {
         if (p.sbufs == 1)
@@ -678,7 +687,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       EPI_BARRIER();
-      if (threadIdx.x == issuer) {
+      if (threadIdx.x == issuer && !(kAblate & 64)) {
         if (wantF) tma_store_3d(&tmF, staging, cc * 32, w0, n0 * p.H + h0);
         if (wantO) {
           tma_store_5d(&tmO, staging + kStageF, 0, w0, h0, cc, n0);
@@ -799,7 +808,11 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
     } else {
       // ---- adjoint: gx = res + (g - mean_C g - a sum_C(g a) / (C - 1)) rstd
       float aa[32];
-      if (valid) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
+      if constexpr ((kAblate & 16) != 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) aa[j] = 0.f;
+      }
+      if (valid && !(kAblate & 16)) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
       const float rstd = valid ? p.epi.ln_rstd_in[pix] : 1.f;
       wait_first();
       float sg = 0.f, sga = 0.f;
@@ -819,7 +832,7 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
         // register buffer, or keeping the request as raw words to convert at use, spills under the 168-register cap
         // of the 320-thread kernel -- with ~28 KB of L1 left beside the shared memory the spill traffic goes to L2
         // and the launch gets 30 % SLOWER.)
-        if (valid && cc + ccstep < nch) {
+        if (valid && cc + ccstep < nch && !(kAblate & 16)) {
           const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
           load32_hilo(an, an + lo_off, aa);
         }
@@ -836,7 +849,11 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       prefetch_tile(tile + nwg * (int)gridDim.x);
       for (int cc = cc0; cc < nch; cc += ccstep) {
         float g[32], a[32];
-        if (!stash && valid) {
+        if constexpr ((kAblate & 16) != 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = 0.f;
+        }
+        if (!stash && valid && !(kAblate & 16)) {
           const bf16* ac = a_pix + (size_t)cc * bs;
           load32_hilo(ac, ac + lo_off, a);
         }
@@ -1282,6 +1299,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
 #pragma unroll
                 for (int half = 0; half < NB; ++half) {
                   const uint32_t accum = (kk | pass) ? 1u : (uint32_t)((chunk | tap) != 0);
+                  if constexpr ((kAblate & 1) != 0) continue;
                   if constexpr (CTA2)
                     umma_bf16_2sm(d0 + half * CB, desc64_patch(al), desc64(bl + half * half_u), idesc, accum);
                   else

@@ -439,6 +439,9 @@ struct FusedGeom {
   static constexpr size_t misc_bytes = (size_t)N * sizeof(float2) + (size_t)N * sizeof(float) +
                                        (size_t)2 * kWarps * (RB + 1) * sizeof(float) + (size_t)kWarps * RB * sizeof(float);
   static constexpr size_t smem_a = slab_bytes + line_bytes + misc_bytes;
+  // packed pair march: both members' slabs, pair-wide flux / v* exchange rows (three blocks per SM: <= 74.6 KB)
+  static constexpr size_t smem_a2 = 2 * slab_bytes + line_bytes + misc_bytes +
+                                    (size_t)2 * kWarps * (RB + 1) * sizeof(float) + (size_t)kWarps * RB * sizeof(float);
   static constexpr int kThreadsC = ((RX * (RB + 1) > N ? RX * (RB + 1) : N) + 31) / 32 * 32;
   static constexpr size_t smem_c = (size_t)(RB + 1) * kLine * sizeof(float2) + (size_t)N * sizeof(float2);
 };
@@ -561,6 +564,192 @@ __global__ void __launch_bounds__(RX* RX)
   }
 #undef U
 #undef V
+  __syncthreads();
+  // FFT along y of the RB lines, RX threads per line
+  for (int line = tid / RX; line < RB; line += N / RX) {
+    const int t = tid % RX;
+    float2* x = zl + line * LS;
+    float2 a[RX];
+#pragma unroll
+    for (int n1 = 0; n1 < RX; ++n1) a[n1] = x[RX * n1 + t];
+    const unsigned grp = line_group_mask(RX);
+    __syncwarp(grp);
+    line_fft_forward<RX>(a, x, tw, t, grp);
+    float2* dst = spec + ((size_t)pair * N + (i0 + line)) * N;
+#pragma unroll
+    for (int k2 = 0; k2 < RX; ++k2) dst[t + RX * k2] = a[k2];
+  }
+}
+
+// ---------------------------------------------------------------------------- packed pair march (Blackwell FFMA2)
+// The two members of a pair run the SAME arithmetic on different data, and sm_100 has two-wide fp32 instructions
+// (add / mul / fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2 on an aligned register pair): the march below carries
+// (member a, member b) in one float2 per quantity, so every add / multiply / fma is ONE issue slot for both
+// members; only compares, selects and the reciprocal stay per component.  The slab holds the members interleaved
+// (one 8-byte shared-memory load per stencil point and pair).  The explicit kernel is bound by instruction issue
+// ("Stepper"): this is where its time goes.
+using f2 = float2;
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0, %1}, rc;}"
+      : "=f"(r.x), "=f"(r.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 splat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float rcp_approx(float a) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ f2 shfl_up2(f2 v) {
+  return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+// face_value for both members (same formula, see face_value)
+__device__ __forceinline__ f2 face_value2(f2 cl, f2 c, f2 cr, f2 cn, f2 uf, f2 ndt_h) {
+  const f2 d = sub2(cr, c);
+  const bool px = uf.x > 0.f, py = uf.y > 0.f;
+  const f2 al = sub2(c, cl), ar = sub2(cn, cr);
+  const f2 a = make_float2(px ? al.x : ar.x, py ? al.y : ar.y);
+  // (no safe denominator here: with d = 0 the test a d > 0 already selects phi = 0, and the limited correction
+  // (high - upwind) phi vanishes with d in either formulation)
+  const f2 ad = mul2(a, d), sum = add2(d, a), two = add2(a, a);
+  const f2 q = mul2(two, make_float2(rcp_approx(sum.x), rcp_approx(sum.y)));
+  const f2 phi = make_float2(ad.x > 0.f ? q.x : 0.f, ad.y > 0.f ? q.y : 0.f);
+  const f2 upwind = make_float2(px ? c.x : cr.x, py ? c.y : cr.y);
+  // high = c + (1 - Cn) d / 2
+  const f2 high = fma2(mul2(fma2(uf, ndt_h, splat(1.f)), splat(0.5f)), d, c);
+  return fma2(sub2(high, upwind), phi, upwind);
+}
+
+// Same work as fused_explicit_rowfft_kernel, both members of the pair marched together.  grid: (N / RB, npairs),
+// block: N threads (one per column).
+template <int RX, int RB>
+__global__ void __launch_bounds__(RX* RX)
+    fused_explicit_rowfft2_kernel(const float* __restrict__ uv, float* __restrict__ uvs, float2* __restrict__ spec,
+                                  int E, float dt, float h, float nu) {
+  using G = FusedGeom<RX, RB>;
+  constexpr int N = G::N, mask = N - 1, SR = G::kSlabRows, LS = G::kLine, NW = G::kWarps;
+  extern __shared__ __align__(16) uint8_t fsm[];
+  f2* su = reinterpret_cast<f2*>(fsm);       // [SR][N] (member a, member b)
+  f2* sv = su + SR * N;                      // [SR][N]
+  float2* zl = sv + SR * N;                  // [RB][LS]
+  float2* tw = zl + RB * LS;                 // [N]
+  float* sforce = reinterpret_cast<float*>(tw + N);  // [N]
+  f2* fyb = reinterpret_cast<f2*>(sforce + N);       // [2][NW][RB + 1]
+  f2* vsb = fyb + 2 * NW * (RB + 1);                 // [NW][RB]
+
+  const int tid = threadIdx.x, j = tid, lane = tid & 31, warp = tid >> 5;
+  const int i0 = blockIdx.x * RB, pair = blockIdx.y;
+  const float inv_h = 1.f / h;
+  const f2 ndt_h = splat(-dt / h), ninv_h = splat(-inv_h), inv_h2 = splat(1.f / (h * h));
+
+  fill_twiddles_full(tw, N, tid, N);
+  sforce[j] = sinf(4.f * ((float)j + 0.5f) * h);  // Kolmogorov forcing at u's offset y_{j+1/2}
+
+  const int ea = 2 * pair, eb = 2 * pair + 1;
+  const bool hasb = eb < E;  // odd ensemble: the missing partner is a zero field whose results are dropped
+  const float* ua = uv + (size_t)ea * 2 * N * N;
+  const float* va = ua + (size_t)N * N;
+  const float* ub = uv + (size_t)(hasb ? eb : ea) * 2 * N * N;
+  const float* vb = ub + (size_t)N * N;
+  for (int idx = tid; idx < SR * (N / 4); idx += N) {
+    const int li = idx / (N / 4), c4 = idx % (N / 4);
+    const int gi = (i0 - 3 + li) & mask;
+    const float4 a = reinterpret_cast<const float4*>(ua + (size_t)gi * N)[c4];
+    const float4 c = reinterpret_cast<const float4*>(va + (size_t)gi * N)[c4];
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), d = b;
+    if (hasb) {
+      b = reinterpret_cast<const float4*>(ub + (size_t)gi * N)[c4];
+      d = reinterpret_cast<const float4*>(vb + (size_t)gi * N)[c4];
+    }
+    float4* du = reinterpret_cast<float4*>(su + li * N + 4 * c4);
+    float4* dv = reinterpret_cast<float4*>(sv + li * N + 4 * c4);
+    du[0] = make_float4(a.x, b.x, a.y, b.y), du[1] = make_float4(a.z, b.z, a.w, b.w);
+    dv[0] = make_float4(c.x, d.x, c.y, d.y), dv[1] = make_float4(c.z, d.z, c.w, d.w);
+  }
+  __syncthreads();
+  // y-face fluxes through the right face of the column left of every warp (lane 0's left face)
+  if (tid < NW * (RB + 1)) {
+    const int w = tid / (RB + 1), k = tid % (RB + 1) - 1;
+    const int jb = (32 * w - 1) & mask;
+#define UB(kk, dj) su[((kk) + 3) * N + ((jb + (dj)) & mask)]
+#define VB(kk, dj) sv[((kk) + 3) * N + ((jb + (dj)) & mask)]
+    const f2 vfu = mul2(add2(VB(k, 0), VB(k + 1, 0)), splat(0.5f));
+    fyb[w * (RB + 1) + k + 1] = mul2(face_value2(UB(k, -1), UB(k, 0), UB(k, 1), UB(k, 2), vfu, ndt_h), vfu);
+    const f2 vfv = mul2(add2(VB(k, 0), VB(k, 1)), splat(0.5f));
+    fyb[(NW + w) * (RB + 1) + k + 1] = mul2(face_value2(VB(k, -1), VB(k, 0), VB(k, 1), VB(k, 2), vfv, ndt_h), vfv);
+#undef UB
+#undef VB
+  }
+  __syncthreads();
+  // march down the column: the flux through the lower x face of a cell is the upper-face flux of the previous
+  // row (register), the left y-face flux comes from the neighbouring lane
+  float* usa = uvs + (size_t)ea * 2 * N * N;
+  float* vsa = usa + (size_t)N * N;
+  float* usb = uvs + (size_t)eb * 2 * N * N;
+  float* vsb_g = usb + (size_t)N * N;
+  f2 fxu_prev = splat(0.f), fxv_prev = splat(0.f), ustar_prev = splat(0.f);
+  const int jm1 = (j - 1) & mask, jp1 = (j + 1) & mask, jp2 = (j + 2) & mask;
+  const f2 force = splat(sforce[j]);
+  const f2 half = splat(0.5f), dt2 = splat(dt), nu2 = splat(nu), drag = splat(-0.1f), m4 = splat(-4.f);
+  const f2* pu = su + N;  // row k of the slab is pu + (k + 2) * N, i.e. these point at row k = -2
+  const f2* pv = sv + N;
+  f2 um1 = pu[-N + j], u00 = pu[j], up1 = pu[N + j];
+  f2 vm1 = pv[-N + j], v00 = pv[j], vp1 = pv[N + j];
+#pragma unroll 2
+  for (int k = -2; k < RB; ++k) {
+    const f2 up2 = pu[2 * N + j], vp2 = pv[2 * N + j];
+    const f2 ur1 = pu[jp1];
+    const f2 ufu = mul2(add2(u00, up1), half);
+    const f2 fxu = mul2(face_value2(um1, u00, up1, up2, ufu, ndt_h), ufu);
+    const f2 ufv = mul2(add2(u00, ur1), half);
+    const f2 fxv = mul2(face_value2(vm1, v00, vp1, vp2, ufv, ndt_h), ufv);
+    if (k >= -1) {
+      const f2 ul1 = pu[jm1], ur2 = pu[jp2];
+      const f2 vl1 = pv[jm1], vr1 = pv[jp1], vr2 = pv[jp2];
+      const f2 vfu = mul2(add2(v00, vp1), half);
+      const f2 fyu = mul2(face_value2(ul1, u00, ur1, ur2, vfu, ndt_h), vfu);
+      const f2 vfv = mul2(add2(v00, vr1), half);
+      const f2 fyv = mul2(face_value2(vl1, v00, vr1, vr2, vfv, ndt_h), vfv);
+      f2 fyu_m = shfl_up2(fyu), fyv_m = shfl_up2(fyv);
+      if (lane == 0) fyu_m = fyb[warp * (RB + 1) + k + 1], fyv_m = fyb[(NW + warp) * (RB + 1) + k + 1];
+      // conv = -((fx - fx_prev) + (fy - fy_m)) / h
+      const f2 conv_u = mul2(add2(sub2(fxu, fxu_prev), sub2(fyu, fyu_m)), ninv_h);
+      const f2 lap_u = mul2(fma2(u00, m4, add2(add2(up1, um1), add2(ur1, ul1))), inv_h2);
+      const f2 ustar = fma2(dt2, add2(fma2(nu2, lap_u, conv_u), fma2(drag, u00, force)), u00);
+      const f2 conv_v = mul2(add2(sub2(fxv, fxv_prev), sub2(fyv, fyv_m)), ninv_h);
+      const f2 lap_v = mul2(fma2(v00, m4, add2(add2(vp1, vm1), add2(vr1, vl1))), inv_h2);
+      const f2 vstar = fma2(dt2, fma2(drag, v00, fma2(nu2, lap_v, conv_v)), v00);
+      const f2 vleft = shfl_up2(vstar);
+      if (k >= 0) {
+        const size_t o = (size_t)(i0 + k) * N + j;
+        usa[o] = ustar.x, vsa[o] = vstar.x;
+        if (hasb) usb[o] = ustar.y, vsb_g[o] = vstar.y;
+        // backward-difference divergence; lane 0 lacks v*(j-1), fixed up below from vsb
+        f2 zp = mul2(add2(sub2(ustar, ustar_prev), lane ? sub2(vstar, vleft) : vstar), splat(inv_h));
+        if (!hasb) zp.y = 0.f;
+        zl[k * LS + j] = zp;
+        if (lane == 31) vsb[warp * RB + k] = vstar;
+      }
+      ustar_prev = ustar;
+    }
+    fxu_prev = fxu, fxv_prev = fxv;
+    um1 = u00, u00 = up1, up1 = up2;
+    vm1 = v00, v00 = vp1, vp1 = vp2;
+    pu += N, pv += N;
+  }
+  __syncthreads();
+  if (tid < NW * RB) {
+    const int w = tid / RB, k = tid % RB;
+    const f2 vl = vsb[((w + NW - 1) % NW) * RB + k];
+    float2& z = zl[k * LS + 32 * w];
+    z.x -= vl.x * inv_h;
+    if (hasb) z.y -= vl.y * inv_h;
+  }
   __syncthreads();
   // FFT along y of the RB lines, RX threads per line
   for (int line = tid / RX; line < RB; line += N / RX) {
@@ -761,10 +950,19 @@ int inner_step_fast(const sdab_kolmogorov* k, float* uv, float* uvs, float2* spe
                                          (int)G::smem_a));
     SDAB_CUDA_CHECK(cudaFuncSetAttribute(fused_rowifft_grad_kernel<RX, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)G::smem_c));
+    SDAB_CUDA_CHECK(cudaFuncSetAttribute(fused_explicit_rowfft2_kernel<RX, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)G::smem_a2));
     attr_set = true;
   }
-  fused_explicit_rowfft_kernel<RX, RB><<<dim3(N / RB, npairs), N, G::smem_a, st>>>(uv, uvs, spec, E, k->dt_inner, k->h, k->nu);
-  SDAB_LAUNCH_CHECK("fused_explicit_rowfft_kernel");
+  // SDAB_KOLMO_PACKED=0: the scalar march (one member after the other), kept as the cross-check of the packed one
+  static const int packed = env_int("SDAB_KOLMO_PACKED", 1);
+  if (packed) {
+    fused_explicit_rowfft2_kernel<RX, RB><<<dim3(N / RB, npairs), N, G::smem_a2, st>>>(uv, uvs, spec, E, k->dt_inner, k->h, k->nu);
+    SDAB_LAUNCH_CHECK("fused_explicit_rowfft2_kernel");
+  } else {
+    fused_explicit_rowfft_kernel<RX, RB><<<dim3(N / RB, npairs), N, G::smem_a, st>>>(uv, uvs, spec, E, k->dt_inner, k->h, k->nu);
+    SDAB_LAUNCH_CHECK("fused_explicit_rowfft_kernel");
+  }
   constexpr size_t smem_b = (size_t)16 * (RX * (RX + 1) + 1) * sizeof(float2) + (size_t)N * sizeof(float2) + (size_t)N * sizeof(float);
   fused_col_solve_kernel<RX><<<dim3(N / 16, npairs), 16 * RX, smem_b, st>>>(spec, k->h);
   SDAB_LAUNCH_CHECK("fused_col_solve_kernel");
