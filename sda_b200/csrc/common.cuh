@@ -13,6 +13,7 @@
 //          [N][2][C/32][4][(H+2)/2][(W+2)/2][32] -- the input format of the stride-2 heads
 //          (sda/nn.py:151-159), again so that each tap is one dense TMA box.
 #pragma once
+#include <cstdlib>
 
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -24,6 +25,22 @@
 #include "../../include/sdab.h"
 
 namespace sdab {
+
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may become resident while its predecessor in the stream is still draining: everything up to pdl_wait() (barrier
+// initialisation, TMEM allocation) overlaps the predecessor's tail, pdl_wait() returns once the predecessor has
+// completed and its memory is visible.  No global memory is read or written before it.  pdl_launch_dependents()
+// lets the NEXT kernel start launching as soon as every CTA of this one has issued it (they only find room as this
+// grid's CTAs retire).  sdab_pdl_enabled(): SDAB_PDL=0 switches the launch attribute off (A/B).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+inline bool pdl_enabled() {
+  static const int on = getenv("SDAB_PDL") ? atoi(getenv("SDAB_PDL")) : 1;
+  return on != 0;
+}
+
 
 // ----------------------------------------------------------------------------- errors
 void set_error(const std::string& msg);

@@ -925,6 +925,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int tile_begin = CTA2 ? 2 * ((int)blockIdx.x >> 1) + (int)rank : (int)blockIdx.x;
   const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -948,6 +949,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  pdl_wait();  // nothing above touches global memory; everything below may read what the previous kernel wrote
   if constexpr (LN != 0) {
     // bias / shift copies for the LayerNorm epilogue (epilogue_ln_role)
     float* cst = reinterpret_cast<float*>(base_ptr + kCtrlBytes);
@@ -1143,6 +1145,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   // LayerNorm they exchange their partial statistics, epilogue_ln_role)
   const bool csplit = (p.acc_stages == 1 || PC > 1 || (LN == 0 && p.csplit)) && blockDim.x == kPatchThreads;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_bfull + 8 * s, 1);
@@ -1170,6 +1173,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  pdl_wait();  // nothing above touches global memory; everything below may read what the previous kernel wrote
   if constexpr (LN != 0) {
     // bias / shift copies for the LayerNorm epilogue (epilogue_ln_role)
     float* cst = reinterpret_cast<float*>(base_ptr + kCtrlBytes);
@@ -1591,14 +1595,22 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(p.patch && patch_wg == 2 ? kPatchThreads : kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SDAB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmF, tmO, p));
   } else {
     const int grid = p.g.num_tiles < num_sms() ? p.g.num_tiles : num_sms();
-    kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmF, tmO, p);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SDAB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmF, tmO, p));
   }
   SDAB_LAUNCH_CHECK("conv_umma_kernel");
   return SDAB_OK;

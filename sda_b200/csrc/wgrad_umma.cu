@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int xchunks = min(4, p.nchunk_x - 4 * mb), gchunks = p.nblk / 32;
   const int ntiles = split < p.num_tiles ? (p.num_tiles - split + p.splits - 1) / p.splits : 0;
 
+  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 96), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();  // nothing above touches global memory
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -499,10 +501,18 @@ int conv3x3_wgrad_umma(const WgradProblem& c, int mode, cudaStream_t stream) {
     attr_set = true;
   }
   const int grid = units * p.splits;
-  if (p.planes == 2)
-    wgrad_umma_kernel<2, 8><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
-  else
-    wgrad_umma_kernel<1, 16><<<grid, kThreads, smem, stream>>>(tmX, tmG, p);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    if (p.planes == 2)
+      SDAB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, wgrad_umma_kernel<2, 8>, tmX, tmG, p));
+    else
+      SDAB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, wgrad_umma_kernel<1, 16>, tmX, tmG, p));
+  }
   SDAB_LAUNCH_CHECK("wgrad_umma_kernel");
   if (p.part) {
     wgrad_reduce_kernel<<<dim3((p.cin + kRedCi - 1) / kRedCi, (p.cout + kRedCo - 1) / kRedCo), kRedCo * kRedCi * p.ntl, 0, stream>>>(p);
