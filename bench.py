@@ -331,6 +331,21 @@ def workload_config(args, world):
     }
 
 
+def exchange_used(score, world):
+    r"""How the window shards were exchanged in this run (what ran, not what was asked for)."""
+
+    if world == 1:
+        return {}
+
+    import sda_b200.score as sc
+
+    bufs = list(score.kernel.network._buffers_mc.values())
+    peer = [b for b in bufs if isinstance(b, sc.PeerExchange)]
+
+    return {'exchange': 'peer-memory all-gather kernel over NVLink (csrc/peer.cu), one launch per exchange' if peer and len(peer) == len(bufs)
+            else 'NCCL all_gather_into_tensor'}
+
+
 # ------------------------------------------------------------------------------------ ours
 def run_ours(args, rank, local_rank, world):
     import ctypes
@@ -351,7 +366,7 @@ def run_ours(args, rank, local_rank, world):
     score = make_score(SIZE, device)
 
     if world > 1:
-        shard_windows(score)
+        shard_windows(score, transport=args.exchange)
 
     x_host, y_host = synthetic(args.batch, LENGTH, SIZE)
     x_pin, y_pin = x_host.pin_memory(), y_host.pin_memory()
@@ -484,7 +499,7 @@ def run_ours(args, rank, local_rank, world):
         'value': value, 'unit': 'steps/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None,
         'dtype': 'bf16x3 (split-bf16 operands, fp32 accumulate)' if passes == 3 else 'bf16 (fp32 accumulate)',
-        'data': 'synthetic', 'config': workload_config(args, world), 'clocks': clocks,
+        'data': 'synthetic', 'config': dict(workload_config(args, world), **exchange_used(score, world)), 'clocks': clocks,
         'e2e': {'value': None if args.profile_run else args.steps / e2e_s, 'unit': 'steps/s', 'h2d_bytes_per_step': x_pin.numel() * 4 + y_pin.numel() * 4,
                 'd2h_bytes_per_step': x_pin.numel() * 4},
         'gpu_launches': int(launches), 'state_sha': state_sha,
@@ -530,6 +545,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=1, help='trajectories sampled together (B)')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='N > 1: exchange of the window shards (peer-memory kernel over NVLink, or NCCL all-gather)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the cpu_baseline and gpu_eager_baseline legs')
     ap.add_argument('--no-secondary', action='store_true', help='skip the stepper / training measurements')
     ap.add_argument('--profile-run', action='store_true', help='for runs under ncu: one warm-up step allowed, no e2e / baseline legs (not a bench value)')

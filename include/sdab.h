@@ -186,6 +186,26 @@ int sdab_unfold_transpose_add(const float* gwin, float* gx, int B, int L, int C,
                               void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * Exchange step of the window-sharded score (the reference is single-GPU, its
+ * MCScoreNet.forward composes the trajectory score from independent window scores, score.py:134-144):
+ * all-gather over NVLink peer memory, one kernel per rank (csrc/peer.cu).
+ * ------------------------------------------------------------------------- */
+
+/* Bytes in front of the payload of a peer buffer (flags, block counter). */
+size_t sdab_peer_header_bytes(void);
+/* cudaMalloc of header + payload_bytes on the current device, header zeroed; handle64 receives the 64-byte CUDA IPC
+ * handle other processes of the box open with sdab_peer_open. */
+int sdab_peer_alloc(size_t payload_bytes, void** ptr, void* handle64);
+int sdab_peer_open(const void* handle64, void** ptr);
+int sdab_peer_close(void* ptr);
+int sdab_peer_free(void* ptr);
+/* bufs[p]: base (header) of rank p's buffer as mapped in THIS process, p < world (host array).  Pushes
+ * [shard_offset, shard_offset + shard_bytes) of the own payload to every peer, signals epoch, returns (on the stream)
+ * when every peer's shard of the same epoch has arrived in the own buffer.  Epochs of one buffer must increase. */
+int sdab_peer_allgather(void* const* bufs, int rank, int world, size_t shard_offset, size_t shard_bytes,
+                        unsigned long long epoch, void* stream);
+
+/* ------------------------------------------------------------------------- *
  * Sampler updates  (reference: sda/score.py:250-261 VPSDE.sample loop body)
  * ------------------------------------------------------------------------- */
 

@@ -69,6 +69,13 @@ _PROTOTYPES = {
     'sdab_fold_transpose': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'sdab_frames_assemble': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'sdab_unfold_transpose_add': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    # exchange over peer memory
+    'sdab_peer_header_bytes': (c_size_t, []),
+    'sdab_peer_alloc': (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    'sdab_peer_open': (c_int, [c_void_p, POINTER(c_void_p)]),
+    'sdab_peer_close': (c_int, [c_void_p]),
+    'sdab_peer_free': (c_int, [c_void_p]),
+    'sdab_peer_allgather': (c_int, [POINTER(c_void_p), c_int, c_int, c_size_t, c_size_t, c_uint64, c_void_p]),
     # sampler
     'sdab_vpsde_predict': (c_int, [c_void_p, c_void_p, c_float, c_float, c_size_t, c_void_p]),
     'sdab_vpsde_correct_scratch_floats': (c_size_t, [c_int]),

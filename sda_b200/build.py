@@ -21,7 +21,7 @@ CSRC = HERE / 'csrc'
 LIB = HERE / 'libsdab.so'
 OBJ = HERE / 'build'
 
-SOURCES = ['api.cu', 'elementwise.cu', 'conv_simt.cu', 'conv_umma.cu', 'unet.cu', 'conv_api.cu', 'score_ops.cu', 'kolmogorov.cu', 'wgrad.cu', 'wgrad_umma.cu']
+SOURCES = ['api.cu', 'elementwise.cu', 'conv_simt.cu', 'conv_umma.cu', 'unet.cu', 'conv_api.cu', 'score_ops.cu', 'kolmogorov.cu', 'wgrad.cu', 'wgrad_umma.cu', 'peer.cu']
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

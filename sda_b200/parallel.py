@@ -119,14 +119,25 @@ class ShardedMCScoreNet(MCScoreNet):
         return self.fold(s, self.order)
 
 
-def shard_windows(score: MCScoreNet, group=None) -> MCScoreNet:
-    r"""Switches `score` (in place) to window-sharded evaluation over `group`."""
+def shard_windows(score: MCScoreNet, group=None, transport: str = 'peer') -> MCScoreNet:
+    r"""Switches `score` (in place) to window-sharded evaluation over `group`.
+
+    transport: how the fused window path exchanges its shards -- 'peer' (default): one kernel per rank over NVLink
+    peer memory (`sda_b200.score.PeerExchange`, all ranks on one box); 'nccl': `all_gather_into_tensor`.  Results
+    are bit-identical either way."""
 
     if not isinstance(score, MCScoreNet):
         raise TypeError('shard_windows expects a MCScoreNet')
 
+    if transport not in ('peer', 'nccl'):
+        raise ValueError("transport must be 'peer' or 'nccl'")
+
     score.__class__ = ShardedMCScoreNet
     score.shard_group = group
+    network = getattr(score.kernel, 'network', None)
+
+    if network is not None:
+        network._shard_transport = transport
 
     return score
 

@@ -219,6 +219,128 @@ def shard_geometry(n_windows: int, windows_per_trajectory: int, order: int, rank
     return begin, end, per, per + 2 * order * touched
 
 
+class _RawCuda:
+    r"""Device memory owned by libsdab, presented to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+
+
+class PeerExchange:
+    r"""The exchange step of the window-sharded score over NVLink peer memory (csrc/peer.cu): two alternating
+    buffers of `shape` fp32 per rank, allocated by the library, exported by CUDA IPC and mapped by every other
+    rank of `group` (all on one box).  `acquire()` hands out the rank's buffer of this turn, `gather()` is ONE kernel
+    that pushes the rank's shard to all peers, signals, and retires when every peer's shard has arrived.
+    Construction is collective; it raises on every rank if any rank cannot map its peers."""
+
+    def __init__(self, shape, group, device):
+        import ctypes
+
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+        self.header = int(lib.sdab_peer_header_bytes())
+        nbytes = 4 * int(torch.Size(shape).numel())
+        self.slots, self.uses, self.turn = [], [0, 0], 0
+        self._own, self._opened = [], []
+        error = None
+
+        with torch.cuda.device(device):
+            for _ in range(2):
+                ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+
+                try:
+                    _lib.check(lib.sdab_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+                    self._own.append(ptr.value)
+                except RuntimeError as e:  # reported collectively below
+                    error = str(e)
+
+                handles = [None] * self.world
+                dist.all_gather_object(handles, None if error else handle.raw, group=group)
+                ptrs = (ctypes.c_void_p * self.world)()
+
+                for p, h in enumerate(handles):
+                    if p == self.rank:
+                        ptrs[p] = ptr.value
+                    elif h is not None and error is None:
+                        q = ctypes.c_void_p()
+
+                        try:
+                            _lib.check(lib.sdab_peer_open(h, ctypes.byref(q)))
+                            self._opened.append(q.value)
+                            ptrs[p] = q.value
+                        except RuntimeError as e:
+                            error = str(e)
+                    else:
+                        error = error or f'rank {p} could not allocate its peer buffer'
+
+                view = None if error else torch.as_tensor(_RawCuda(ptr.value + self.header, nbytes), device=device).view(torch.float32).view(shape)
+                self.slots.append((view, ptrs))
+
+        errors = [None] * self.world
+        dist.all_gather_object(errors, error, group=group)
+
+        if any(errors):
+            self.close()
+            raise RuntimeError('peer-memory exchange unavailable: ' + '; '.join(f'rank {p}: {e}' for p, e in enumerate(errors) if e))
+
+    def acquire(self) -> Tensor:
+        self.turn ^= 1
+        self.uses[self.turn] += 1
+
+        return self.slots[self.turn][0]
+
+    def gather(self, shard_offset_bytes: int, shard_bytes: int) -> None:
+        r"""Completes the buffer handed out by the last `acquire()` (enqueued on the current stream)."""
+
+        _, ptrs = self.slots[self.turn]
+        _lib.check(_lib.load().sdab_peer_allgather(ptrs, self.rank, self.world, shard_offset_bytes, shard_bytes, self.uses[self.turn], _lib.stream_ptr()))
+
+    def close(self) -> None:
+        lib = _lib.load()
+
+        for q in self._opened:
+            lib.sdab_peer_close(q)
+
+        for q in self._own:
+            lib.sdab_peer_free(q)
+
+        self._opened, self._own, self.slots = [], [], []
+
+
+def _exchange(net: UNet, key, shape, group, device):
+    r"""Persistent exchange buffers of `net` for `key`: a PeerExchange (transport 'peer', the default of
+    sda_b200.parallel.shard_windows) or a plain tensor for NCCL's all_gather_into_tensor (transport 'nccl',
+    SDAB_PEER_GATHER=0, or after the peer mapping failed -- with a warning, on every rank alike)."""
+
+    ex = net._buffers_mc.get(key)
+
+    if ex is None:
+        import os
+
+        transport = getattr(net, '_shard_transport', 'peer')
+
+        if os.environ.get('SDAB_PEER_GATHER', '1') == '0':
+            transport = 'nccl'
+
+        if transport == 'peer':
+            try:
+                ex = PeerExchange(shape, group, device)
+            except RuntimeError as e:
+                import warnings
+
+                warnings.warn(f'{e} -- falling back to NCCL all-gather')
+                net._shard_transport = 'nccl'
+
+        if ex is None:
+            ex = torch.empty(shape, dtype=torch.float32, device=device)
+
+        net._buffers_mc[key] = ex
+
+    return ex
+
+
 class _MCScore(torch.autograd.Function):
     r"""MCScoreNet.forward (sda/score.py:134-144) as one library call per rank: unfold, the context concat and
     fold are addressing inside the network's first and last layer.  Window-sharded (group of > 1 ranks): every
@@ -245,16 +367,17 @@ class _MCScore(torch.autograd.Function):
         if world == 1:
             net._native_mcscore_forward(x, y, cvals, order, 0, B * nw, out, 0, 0, save)
         else:
-            key = ('fwd', world, cap, C, H, W, x.device)
-            buf = net._buffers_mc.get(key)
-
-            if buf is None:
-                buf = net._buffers_mc[key] = torch.empty((world * cap, C, H, W), dtype=torch.float32, device=x.device)
+            ex = _exchange(net, ('fwd', world, cap, C, H, W, x.device), (world * cap, C, H, W), group, x.device)
+            buf = ex.acquire() if isinstance(ex, PeerExchange) else ex
 
             if end > begin:
                 net._native_mcscore_forward(x, y, cvals, order, begin, end, buf[rank * cap:], per, cap, save)
 
-            dist.all_gather_into_tensor(buf, buf[rank * cap:(rank + 1) * cap], group=group)
+            if isinstance(ex, PeerExchange):
+                with torch.cuda.device(x.device):
+                    ex.gather(rank * cap * C * H * W * 4, cap * C * H * W * 4)
+            else:
+                dist.all_gather_into_tensor(buf, buf[rank * cap:(rank + 1) * cap], group=group)
 
             with torch.cuda.device(x.device):
                 _lib.check(lib.sdab_frames_assemble(buf.data_ptr(), out.data_ptr(), B, L, C, H, W, order, per, cap, _lib.stream_ptr()))
@@ -282,16 +405,27 @@ class _MCScore(torch.autograd.Function):
 
         g = g.detach().to(torch.float32).contiguous()
         B, L, C, H, W = g.shape
-        key = ('bwd', world, per, C, H, W, g.device)
-        gwin = net._buffers_mc.get(key)
+        key, shape = ('bwd', world, per, C, H, W, g.device), (world * per, (2 * order + 1) * C, H, W)
 
-        if gwin is None:
-            gwin = net._buffers_mc[key] = torch.empty((world * per, (2 * order + 1) * C, H, W), dtype=torch.float32, device=g.device)
+        if world > 1:
+            ex = _exchange(net, key, shape, group, g.device)
+        else:
+            ex = net._buffers_mc.get(key)
+
+            if ex is None:
+                ex = net._buffers_mc[key] = torch.empty(shape, dtype=torch.float32, device=g.device)
+
+        gwin = ex.acquire() if isinstance(ex, PeerExchange) else ex
 
         if end > begin:
             net._native_mcscore_dgrad(g, gwin, Cc, order, begin, end)
 
-        if world > 1:
+        if isinstance(ex, PeerExchange):
+            shard = per * (2 * order + 1) * C * H * W * 4
+
+            with torch.cuda.device(g.device):
+                ex.gather(rank * shard, shard)
+        elif world > 1:
             dist.all_gather_into_tensor(gwin, gwin[rank * per:(rank + 1) * per], group=group)
 
         gx = torch.empty_like(g)

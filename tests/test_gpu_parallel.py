@@ -29,7 +29,8 @@ def _worker(rank, world, port, results):
 
         ok = True
 
-        for B, L in ((1, 9), (2, 6)):   # 7 windows: uneven 4 / 3 split; 2 x 4 windows: one trajectory per rank
+        for transport, (B, L) in ((tr, bl) for tr in ('peer', 'nccl') for bl in ((1, 9), (2, 6))):
+            # 7 windows: uneven 4 / 3 split; 2 x 4 windows: one trajectory per rank
             score, k = build_score('net_small', 32, 'cuda')
             x = randn((B, L, 2, 32, 32), seed=1).cuda()
             y = randn((B, L, 2, 16, 16), seed=2).cuda()
@@ -42,11 +43,17 @@ def _worker(rank, world, port, results):
             with torch.no_grad():
                 plain = score(x, t)
             plain_g = guided(score)
-            shard_windows(score)
-            with torch.no_grad():
-                sharded = score(x, t)
-            sharded_g = guided(score)
-            ok = ok and bool(torch.equal(plain, sharded) and torch.equal(plain_g, sharded_g))
+            shard_windows(score, transport=transport)
+
+            for _ in range(3):  # the peer exchange alternates two buffers: several turns of each
+                with torch.no_grad():
+                    sharded = score(x, t)
+                sharded_g = guided(score)
+                ok = ok and bool(torch.equal(plain, sharded) and torch.equal(plain_g, sharded_g))
+
+            # the transport that was asked for is the one that ran (no silent fallback to NCCL)
+            peers = [v for v in score.kernel.network._buffers_mc.values() if isinstance(v, sc.PeerExchange)]
+            ok = ok and (len(peers) == 2 if transport == 'peer' else not peers)
             # the materialised fallback of the sharded path (per-window kernels that are not fusable)
             score.fuse_windows = False
             with torch.no_grad():
