@@ -38,7 +38,12 @@ namespace {
 #endif
 constexpr int kAblate = SDAB_ABLATE;
 constexpr int kThreads = 192;
-constexpr int kPatchThreads = 320;  // patch kernel: two epilogue warpgroups (warps 2-5 and 6-9)
+// patch kernel: warpgroup 0 = TMA producer (warp 0), MMA issuer (warp 1) and two idle warps, warpgroups 1 and 2 =
+// the two epilogue warpgroups (warps 4-7 and 8-11).  The roles sit on hardware warpgroup boundaries so that the
+// register file can be re-divided (setmaxnreg): 56 registers per thread for warpgroup 0, 224 for the epilogue --
+// 128 x 56 + 256 x 224 = 64512, what a 384-thread CTA launched at 168 owns.
+constexpr int kPatchThreads = 384;
+constexpr int kPatchEpi0 = 128;  // first epilogue thread of the patch kernel (64 in conv_umma_kernel)
 constexpr uint32_t kABytes = 128 * 64;  // one A box: 128 pixels x 32 channels x bf16
 constexpr uint32_t kCtrlBytes = 1024;
 // LayerNorm kernels: bias[512] and shift[512] copies, then the csplit statistics exchange, behind the control block
@@ -82,6 +87,7 @@ struct UmmaParams {
   int nsplit;      // patch kernel, C_out > 256 without LayerNorm: a work item is (tile, half of the output channels)
   int item_chunks; // 32-channel blocks of one work item (out_chunks / nsplit)
   int csplit;      // patch kernel: epilogue warpgroups split channel blocks even with a double-buffered accumulator
+  int epi_wgs;     // patch kernel: epilogue warpgroups in use (2; SDAB_UMMA_WG=1 leaves the second one idle)
   int pieces;      // patch kernel, C_out = 384 with a fused LayerNorm: the accumulator of a tile is built as `pieces`
                    // consecutive N = CB items in a ring of acc_stages TMEM slots (1: one item per tile)
   uint32_t ctrl_bytes;  // control block in front of the staging tiles (barriers, TMEM slot, csplit statistics exchange)
@@ -363,15 +369,16 @@ template <bool CTA2>
 __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtensorMap& tmF, const CUtensorMap& tmO,
                                               uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
                                               uint32_t acc_stride, uint32_t staging_base, int tile_begin, int tile_end,
-                                              int warp, int lane, int wg = 0, int nwg = 1, bool csplit = false) {
+                                              int warp, int lane, int wg = 0, int nwg = 1, bool csplit = false,
+                                              int epi0 = 64) {
   // `nwg` epilogue warpgroups, each with its own staging sets, named barrier and store-issuing thread (its
   // first).  They take alternate tiles (warpgroup wg always drains TMEM accumulator wg), or -- csplit, for
   // the single-accumulator case (C_out > 256) without LayerNorm -- alternate 32-channel blocks of every tile.
   const uint32_t staging0 = staging_base + wg * p.sbufs * kStagingBytes;
-  const int issuer = 64 + 128 * wg;
+  const int issuer = epi0 + 128 * wg;
   const int cc0 = csplit ? wg : 0, ccstep = csplit ? nwg : 1;
+  const int bar_id = wg;
   if (csplit) wg = 0, nwg = 1;  // tile walk of a single warpgroup
-  const int bar_id = issuer >> 7;  // == original wg
   const int q = warp & 3;  // TMEM lane quarter accessible to this warp
   const int m = q * 32 + lane;
   const int bw = m % p.g.BW, bh = (m / p.g.BW) % p.g.BH, bn = m / (p.g.BW * p.g.BH);
@@ -548,9 +555,9 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
                                                  uint32_t bar_tfull, uint32_t bar_tempty, uint32_t tmem_base,
                                                  uint32_t acc_stride, uint32_t staging_base, const float* cst,
                                                  float2* xchg, int tile_begin, int tile_end, int warp, int lane, int wg, int nwg,
-                                                 bool csplit) {
+                                                 bool csplit, int epi0 = 64) {
   const uint32_t staging0 = staging_base + wg * p.sbufs * kStagingBytes;
-  const int issuer = 64 + 128 * wg;
+  const int issuer = epi0 + 128 * wg;
   const int bar_id = wg;
   const int half = wg;  // csplit: this warpgroup takes channel blocks half, half + 2, ...
   const int cc0 = csplit ? wg : 0, ccstep = csplit ? nwg : 1;
@@ -1143,7 +1150,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   const int tile_end = CTA2 ? p.g.num_tiles + (int)rank : p.g.num_tiles;
   // single accumulator (C_out > 256): the two epilogue warpgroups split every tile's channel blocks (with a fused
   // LayerNorm they exchange their partial statistics, epilogue_ln_role)
-  const bool csplit = (p.acc_stages == 1 || PC > 1 || (LN == 0 && p.csplit)) && blockDim.x == kPatchThreads;
+  const bool csplit = (p.acc_stages == 1 || PC > 1 || (LN == 0 && p.csplit)) && p.epi_wgs == 2;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) {
@@ -1193,6 +1200,10 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
   // pair-items of this launch (item_of); for nsplit == 1 "(vt >> 1) < v_end" is "tile < tile_end"
   const int v_end = ((p.g.num_tiles + 1) >> 1) * p.nsplit;
 
+  // (each setmaxnreg sits INSIDE the branch it governs: after a join of the two, ptxas allocates everything that
+  // follows under the smaller of the two limits)
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ===================================================================== TMA producer
     // Issue order: patch of K-block g + 1, then the nine weight blocks of K-block g, so that the
@@ -1328,19 +1339,21 @@ __global__ void __launch_bounds__(kPatchThreads, 1)
         if (++as == p.a_stages) as = 0, aph ^= 1;
       }
     }
+  }
   } else {
-    // ===================================================================== epilogue (warps 2..5, 6..9)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    // ===================================================================== epilogue (warps 4..7, 8..11)
     // with a double-buffered accumulator the two warpgroups take alternate tiles
-    const int wg = (warp - 2) >> 2, nwg = ((p.acc_stages == 2 || csplit) && blockDim.x == kPatchThreads) ? 2 : 1;
+    const int wg = (warp - 4) >> 2, nwg = ((p.acc_stages == 2 || csplit) && p.epi_wgs == 2) ? 2 : 1;
     if (wg < nwg) {
       if constexpr (LN != 0)
         epilogue_ln_role<LN, CTA2, PC>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0,
                                        reinterpret_cast<const float*>(base_ptr + kCtrlBytes),
                                        reinterpret_cast<float2*>(base_ptr + kCtrlBytes + kCstBytes), tile_begin, tile_end,
-                                       warp, lane, wg, nwg, csplit);
+                                       warp, lane, wg, nwg, csplit, kPatchEpi0);
       else
         epilogue_role<CTA2>(p, tmF, tmO, bar_tfull, bar_tempty, tmem_base, acc_stride, staging0, tile_begin, tile_end,
-                            warp, lane, wg, nwg, csplit);
+                            warp, lane, wg, nwg, csplit, kPatchEpi0);
     }
   }
 
@@ -1470,6 +1483,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
   static const int patch_wg = getenv("SDAB_UMMA_WG") ? atoi(getenv("SDAB_UMMA_WG")) : 2;  // epilogue warpgroups
   static const int csplit_env = getenv("SDAB_UMMA_CSPLIT") ? atoi(getenv("SDAB_UMMA_CSPLIT")) : 0;
   p.csplit = csplit_env;
+  p.epi_wgs = patch_wg == 2 ? 2 : 1;
   SDAB_REQUIRE(c.epi.ln != 1 || (!c.epi.act && !c.epi.dact && !c.epi.pre),
                "the fused forward LayerNorm follows a plain (bias / residual) convolution");
   p.patch = patch_ok;
@@ -1594,7 +1608,7 @@ int conv3x3_umma(const ConvProblem& c, cudaStream_t stream) {
     const int pairs = (p.g.num_tiles + 1) / 2 * p.nsplit;  // pair-items
     const int clusters = pairs < num_sms() / 2 ? pairs : num_sms() / 2;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(p.patch && patch_wg == 2 ? kPatchThreads : kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+    cfg.gridDim = dim3(2 * clusters), cfg.blockDim = dim3(p.patch ? kPatchThreads : kThreads), cfg.dynamicSmemBytes = smem, cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
