@@ -323,7 +323,8 @@ __device__ __forceinline__ void epilogue_math32(const ConvEpilogue& e, float (&v
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
-// 32 consecutive floats / the 32-channel hi+lo value of one pixel with 16 B loads
+
+// 32 consecutive floats of one pixel with 16 B loads
 __device__ __forceinline__ void load32(const float* __restrict__ src, float (&o)[32]) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -331,21 +332,6 @@ __device__ __forceinline__ void load32(const float* __restrict__ src, float (&o)
     o[4 * j] = t.x, o[4 * j + 1] = t.y, o[4 * j + 2] = t.z, o[4 * j + 3] = t.w;
   }
 }
-__device__ __forceinline__ void load32_hilo(const bf16* __restrict__ hi, const bf16* __restrict__ lo, float (&o)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint4 a = *reinterpret_cast<const uint4*>(hi + 8 * j);
-    const uint4 b = *reinterpret_cast<const uint4*>(lo + 8 * j);
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // bf16 -> fp32 is a 16-bit shift
-      o[8 * j + 2 * k] = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
-      o[8 * j + 2 * k + 1] = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
-    }
-  }
-}
-
 
 // Work items of the CTA-pair kernels.  The loop index vt runs over "virtual tiles": pair-item v = vt >> 1 of CTA
 // vt & 1 of the pair.  With nsplit == 1 an item is a tile (vt IS the tile index); with nsplit == 2 the pair-item
@@ -533,6 +519,30 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
     }
   }
   if (p.staged && threadIdx.x == issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// The hi / lo words of 32 channels as loaded: converting them (load32_hilo) right after the request makes the
+// thread wait for the data on the spot, so a request issued ahead of its use stays raw until then.
+struct RawHiLo {
+  uint4 h[4], l[4];
+};
+__device__ __forceinline__ void load_raw_hilo(const bf16* __restrict__ hi, const bf16* __restrict__ lo, RawHiLo& r) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    r.h[j] = *reinterpret_cast<const uint4*>(hi + 8 * j);
+    r.l[j] = *reinterpret_cast<const uint4*>(lo + 8 * j);
+  }
+}
+__device__ __forceinline__ void convert_hilo(const RawHiLo& r, float (&o)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t aw[4] = {r.h[j].x, r.h[j].y, r.h[j].z, r.h[j].w}, bw[4] = {r.l[j].x, r.l[j].y, r.l[j].z, r.l[j].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[8 * j + 2 * k] = __uint_as_float(aw[k] << 16) + __uint_as_float(bw[k] << 16);
+      o[8 * j + 2 * k + 1] = __uint_as_float(aw[k] & 0xFFFF0000u) + __uint_as_float(bw[k] & 0xFFFF0000u);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ LayerNorm epilogue
@@ -814,20 +824,31 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       }
     } else {
       // ---- adjoint: gx = res + (g - mean_C g - a sum_C(g a) / (C - 1)) rstd
-      float aa[32];
-      if constexpr ((kAblate & 16) != 0) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) aa[j] = 0.f;
-      }
-      if (valid && !(kAblate & 16)) load32_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, aa);
+      // Operand requests run one block ahead of their use and stay RAW until then (converting at the request makes
+      // the thread wait for the data on the spot); the residual has two blocks in flight.  (This needs the 224
+      // registers the epilogue warpgroups own since the roles sit on warpgroup boundaries: under the former
+      // 168-register cap the second buffer spilled and the launch got 30 % slower.)
+      constexpr bool kNoOperands = (kAblate & 16) != 0;
+      RawHiLo raw;
+      if (valid && !kNoOperands) load_raw_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, raw);
       const float rstd = valid ? p.epi.ln_rstd_in[pix] : 1.f;
       wait_first();
       float sg = 0.f, sga = 0.f;
       for (int cc = cc0; cc < nch; cc += ccstep) {
-        float g[32];
+        float g[32], aa[32];
         wait_block(cc);
         tmem_ld32(col_of(cc), g);
         if (valid) {
+          if constexpr (kNoOperands) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) aa[j] = 0.f;
+          } else {
+            convert_hilo(raw, aa);
+            if (cc + ccstep < nch) {
+              const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
+              load_raw_hilo(an, an + lo_off, raw);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             sg += g[j];
@@ -835,17 +856,11 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
           }
         }
         if (stash) tmem_st32(ts + cc * 32, aa);
-        // consumed: request the next block of a, it arrives during the next accumulator load.  (Measured: a second
-        // register buffer, or keeping the request as raw words to convert at use, spills under the 168-register cap
-        // of the 320-thread kernel -- with ~28 KB of L1 left beside the shared memory the spill traffic goes to L2
-        // and the launch gets 30 % SLOWER.)
-        if (valid && cc + ccstep < nch && !(kAblate & 16)) {
-          const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
-          load32_hilo(an, an + lo_off, aa);
-        }
       }
+      // operands of the second sweep: the first residual block, and (no stash) the first block of a again
       float rr[32];
       if (has_res) load32(resp + cc0 * 32, rr);
+      if (!stash && valid && !kNoOperands) load_raw_hilo(a_pix + (size_t)cc0 * bs, a_pix + (size_t)cc0 * bs + lo_off, raw);
       if (csplit) {
         float2 p0, p1;
         exchange(sg, sga, p0, p1);
@@ -855,25 +870,34 @@ __device__ __forceinline__ void epilogue_ln_role(const UmmaParams& p, const CUte
       if (stash) tmem_st_wait();
       prefetch_tile(tile + nwg * (int)gridDim.x);
       for (int cc = cc0; cc < nch; cc += ccstep) {
-        float g[32], a[32];
-        if constexpr ((kAblate & 16) != 0) {
+        {
+          {
+            float g[32], a[32];
+            tmem_ld32(col_of(cc), g);
+            if (stash) {
+              tmem_ld32(ts + cc * 32, a);
+            } else if (valid) {
+              if constexpr (kNoOperands) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a[j] = 0.f;
-        }
-        if (!stash && valid && !(kAblate & 16)) {
-          const bf16* ac = a_pix + (size_t)cc * bs;
-          load32_hilo(ac, ac + lo_off, a);
-        }
-        tmem_ld32(col_of(cc), g);
-        if (stash) tmem_ld32(ts + cc * 32, a);
-        release_after(cc);
-        if (valid) {
+                for (int j = 0; j < 32; ++j) a[j] = 0.f;
+              } else {
+                convert_hilo(raw, a);
+                if (cc + ccstep < nch) {
+                  const bf16* an = a_pix + (size_t)(cc + ccstep) * bs;
+                  load_raw_hilo(an, an + lo_off, raw);
+                }
+              }
+            }
+            release_after(cc);
+            if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) g[j] = (g[j] - mg - a[j] * beta) * rstd + (has_res ? rr[j] : 0.f);
+              for (int j = 0; j < 32; ++j) g[j] = (g[j] - mg - a[j] * beta) * rstd + (has_res ? rr[j] : 0.f);
+            }
+            // the residual of this block is consumed: request the next block's while this one is staged
+            if (has_res && cc + ccstep < nch) load32(resp + (cc + ccstep) * 32, rr);
+            stage_and_store(cc, g, [](float (&)[32]) {});
+          }
         }
-        // the residual of this block is consumed: request the next block's while this one is staged
-        if (has_res && cc + ccstep < nch) load32(resp + (cc + ccstep) * 32, rr);
-        stage_and_store(cc, g, [](float (&)[32]) {});
       }
     }
   }
