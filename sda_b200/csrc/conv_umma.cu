@@ -385,6 +385,16 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
     const int n = n0 + bn, h = p.os * (h0 + bh) + p.oh0, w = p.os * (w0 + bw) + p.ow0;
     const bool valid = n < p.N;
     const size_t pix = ((size_t)n * p.Ho + h) * p.Wo + w;
+    // developer ablation bits: 16 = no global operand loads, 32 = no stores
+    const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16) && !(kAblate & 16),
+               has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16) && !(kAblate & 16);
+    // the global operand (residual or saved pre-activation) of a block is requested one block ahead of its use: the
+    // first one here, before the accumulator is waited for, the next ones as soon as the previous is consumed
+    float rr[32];
+    if (p.staged && !(p.debug & 4)) {
+      if (has_res) load32(p.epi.res + pix * p.Cout + (nh * nchunks + cc0) * 32, rr);
+      if (has_dact) load32(p.epi.dact + pix * p.Cout + (nh * nchunks + cc0) * 32, rr);
+    }
     mbar_wait(bar_tfull + 8 * acc, acc_phase);
     tc_fence_after();
     const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_stride;
@@ -404,9 +414,6 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
       const bool wantO = p.epi.outOP != nullptr;
       const bool edge = valid && (h == 0 || h == p.Ho - 1 || w == 0 || w == p.Wo - 1);
       const OpShape so{0, p.Ho, p.Wo, p.Cout, 0};
-      // developer ablation bits: 16 = no global operand loads, 32 = no stores
-      const bool has_res = p.epi.res != nullptr && valid && !(p.debug & 16) && !(kAblate & 16),
-                 has_dact = p.epi.dact != nullptr && valid && !(p.debug & 16) && !(kAblate & 16);
       {
         // pull the next item's epilogue operands of this pixel row into L2 one item ahead
         const int nvt = vt + nwg * (int)gridDim.x;
@@ -426,10 +433,7 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
       }
       for (int cc = cc0; cc < nchunks; cc += ccstep) {
         const int gc = gc0 + cc;  // block index in the output tensor; cc indexes the accumulator columns
-        float v[32], f[32], rr[32];
-        // operands from global memory first: their latency overlaps the accumulator load
-        if (has_res) load32(p.epi.res + pix * p.Cout + gc * 32, rr);
-        if (has_dact) load32(p.epi.dact + pix * p.Cout + gc * 32, rr);
+        float v[32], f[32];
         tmem_ld32(t0 + cc * 32, v);
         if (cc + ccstep >= nchunks) {
           // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp
@@ -443,6 +447,10 @@ __device__ __forceinline__ void epilogue_role(const UmmaParams& p, const CUtenso
           }
         }
         epilogue_math32(p.epi, v, f, rr, has_res, has_dact, gc * 32);
+        if (cc + ccstep < nchunks) {
+          if (has_res) load32(p.epi.res + pix * p.Cout + (gc + ccstep) * 32, rr);
+          if (has_dact) load32(p.epi.dact + pix * p.Cout + (gc + ccstep) * 32, rr);
+        }
         if ((p.debug & 32) || (kAblate & 32)) continue;
         // staging set `sbuf` free again?  (the TMA stores issued sbufs blocks ago have read it)
         const uint32_t staging = staging0 + sbuf * kStagingBytes;
