@@ -204,6 +204,17 @@ int sdab_peer_free(void* ptr);
  * when every peer's shard of the same epoch has arrived in the own buffer.  Epochs of one buffer must increase. */
 int sdab_peer_allgather(void* const* bufs, int rank, int world, size_t shard_offset, size_t shard_bytes,
                         unsigned long long epoch, void* stream);
+/* Announces `epoch` in every peer's header and waits (on the stream) for every peer's announcement: "my buffer is
+ * complete" -- e.g. the gradients of loss.backward() before sdab_peer_adamw reads them over NVLink. */
+int sdab_peer_signal_wait(void* const* bufs, int rank, int world, unsigned long long epoch, void* stream);
+/* Data-parallel optimizer.step() of torch.optim.AdamW (the optimizer of sda/utils.py:125-143) for the slice
+ * [begin, end) of the flat parameter vector owned by `rank`: gradient = mean over the ranks of grad_bufs[p] (read
+ * over NVLink, added in rank order), AdamW on the slice (m, v: the slice's moments, end - begin floats), the new
+ * parameters stored into EVERY rank's param_bufs[p]; returns (on the stream) when the other ranks' slices have
+ * arrived in the own parameter buffer.  world == 1: a plain fused AdamW over [begin, end).  step counts from 1. */
+int sdab_peer_adamw(void* const* grad_bufs, void* const* param_bufs, float* m, float* v, size_t begin, size_t end,
+                    int rank, int world, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    unsigned long long epoch, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * Sampler updates  (reference: sda/score.py:250-261 VPSDE.sample loop body)

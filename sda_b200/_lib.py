@@ -76,6 +76,9 @@ _PROTOTYPES = {
     'sdab_peer_close': (c_int, [c_void_p]),
     'sdab_peer_free': (c_int, [c_void_p]),
     'sdab_peer_allgather': (c_int, [POINTER(c_void_p), c_int, c_int, c_size_t, c_size_t, c_uint64, c_void_p]),
+    'sdab_peer_signal_wait': (c_int, [POINTER(c_void_p), c_int, c_int, c_uint64, c_void_p]),
+    'sdab_peer_adamw': (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_size_t, c_int, c_int,
+                                c_float, c_float, c_float, c_float, c_float, c_int, c_uint64, c_void_p]),
     # sampler
     'sdab_vpsde_predict': (c_int, [c_void_p, c_void_p, c_float, c_float, c_size_t, c_void_p]),
     'sdab_vpsde_correct_scratch_floats': (c_size_t, [c_int]),

@@ -334,6 +334,25 @@ int ln_backward(const float* ga, const bf16* a_op, const float* rstd, const floa
 int time_shifts(const float* y, const float* pw, const float* pb, float* out, int Nt, int rows, int mod,
                 cudaStream_t st);
 int pack_conv_weights(const float* w, bf16* fwd, bf16* bwd, int Cout, int Cin, cudaStream_t st);
+// the same for up to kMaxPack convolutions in one launch, and up to kMaxCopy zero-padded copies in one launch
+constexpr int kMaxPack = 64, kMaxCopy = 96;
+struct PackTable {
+  const float* w[kMaxPack];
+  bf16* fwd[kMaxPack];
+  bf16* bwd[kMaxPack];
+  int cout[kMaxPack], cin[kMaxPack];
+  unsigned long long start[kMaxPack + 1];
+  int n;
+};
+struct CopyTable {
+  const float* src[kMaxCopy];
+  float* dst[kMaxCopy];
+  int n_src[kMaxCopy], n_dst[kMaxCopy];
+  unsigned long long start[kMaxCopy + 1];
+  int n;
+};
+int pack_conv_weights_batched(PackTable& t, cudaStream_t st);
+int copy_pad_batched(CopyTable& t, cudaStream_t st);
 int pack_tail_weights(const float* w, bf16* tf, bf16* tb, int Cout, int Cin, cudaStream_t st);
 int copy_f32(const float* src, float* dst, size_t n, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);

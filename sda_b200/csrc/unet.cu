@@ -266,20 +266,43 @@ int sdab_unet_set_weights(sdab_unet* h, const float* const* conv_w, const float*
   SDAB_TRY(sdab_device_check());
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* base = (uint8_t*)packed;
+  // every convolution in one pack launch per kMaxPack layers, every small copy (zero-padded biases, projection
+  // weights and biases) in one copy launch per kMaxCopy entries: a training step repacks after every optimizer step
+  PackTable pt{};
+  CopyTable ct{};
+  auto flush_pack = [&]() -> int {
+    if (pt.n) SDAB_TRY(pack_conv_weights_batched(pt, st));
+    pt.n = 0;
+    return SDAB_OK;
+  };
+  auto add_copy = [&](const float* src, float* dst, size_t n_src, size_t n_dst) -> int {
+    if (ct.n == kMaxCopy) {
+      SDAB_TRY(copy_pad_batched(ct, st));
+      ct.n = 0;
+    }
+    ct.src[ct.n] = src, ct.dst[ct.n] = dst, ct.n_src[ct.n] = (int)n_src, ct.n_dst[ct.n] = (int)n_dst;
+    ++ct.n;
+    return SDAB_OK;
+  };
   for (size_t i = 0; i < h->convs.size(); ++i) {
     const ConvLayer& c = h->convs[i];
-    SDAB_TRY(pack_conv_weights(conv_w[i], (bf16*)(base + c.off_fwd), (bf16*)(base + c.off_bwd), c.cout, c.cin, st));
+    if (pt.n == kMaxPack) SDAB_TRY(flush_pack());
+    pt.w[pt.n] = conv_w[i], pt.fwd[pt.n] = (bf16*)(base + c.off_fwd), pt.bwd[pt.n] = (bf16*)(base + c.off_bwd);
+    pt.cout[pt.n] = c.cout, pt.cin[pt.n] = c.cin;
+    ++pt.n;
     if (c.is_tail)
       SDAB_TRY(pack_tail_weights(conv_w[i], (bf16*)(base + c.off_tf), (bf16*)(base + c.off_tb), c.cout, c.cin, st));
-    SDAB_TRY(fill_zero(base + c.off_bias, (size_t)c.nf * sizeof(float), st));
-    SDAB_TRY(copy_f32(conv_b[i], (float*)(base + c.off_bias), c.cout, st));
+    SDAB_TRY(add_copy(conv_b[i], (float*)(base + c.off_bias), c.cout, c.nf));
   }
+  SDAB_TRY(flush_pack());
   const int mod = h->d.mod_features;
   for (size_t j = 0; j < h->block_ch.size(); ++j) {
     const size_t r0 = h->block_shift_off[j];
-    SDAB_TRY(copy_f32(proj_w[j], (float*)(base + h->off_projw) + r0 * mod, (size_t)h->block_ch[j] * mod, st));
-    SDAB_TRY(copy_f32(proj_b[j], (float*)(base + h->off_projb) + r0, h->block_ch[j], st));
+    SDAB_TRY(add_copy(proj_w[j], (float*)(base + h->off_projw) + r0 * mod, (size_t)h->block_ch[j] * mod,
+                      (size_t)h->block_ch[j] * mod));
+    SDAB_TRY(add_copy(proj_b[j], (float*)(base + h->off_projb) + r0, h->block_ch[j], h->block_ch[j]));
   }
+  if (ct.n) SDAB_TRY(copy_pad_batched(ct, st));
   h->packed = base;
   h->weights_set = true;
   h->saved = false;

@@ -218,6 +218,21 @@ class _UNetFunction(torch.autograd.Function):
         )
 
 
+_optimizer_steps = [0]
+
+
+def _count_optimizer_step(optimizer, args, kwargs) -> None:
+    _optimizer_steps[0] += 1
+
+
+try:  # global post-step hook of torch.optim (every optimizer instance, present and future)
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+
+    register_optimizer_step_post_hook(_count_optimizer_step)
+except ImportError:  # pragma: no cover -- older torch: fused optimizers then need UNet.invalidate_packed()
+    pass
+
+
 class UNet(nn.Module):
     r"""U-Net with additive time modulation.  Reference: sda/nn.py:74-206.
 
@@ -362,6 +377,7 @@ class UNet(nn.Module):
             state[k] = None
 
         state['_buffers_mc'] = {}
+        state['_grad_target'] = None
         state['_grad_flat'] = None
 
         return state
@@ -370,7 +386,8 @@ class UNet(nn.Module):
         r"""Forces the bf16-packed weight copies to be rebuilt at the next forward.  The cache is keyed on
         (data_ptr, version) of every parameter, which in-place updates through `.data` (EMA, weight
         surgery) do not change: call this after such an update.  `load_state_dict`, `.to()`, `.cuda()`
-        and friends call it themselves.  SDAB_ALWAYS_REPACK=1 repacks at every forward."""
+        and friends call it themselves, and every `torch.optim.Optimizer.step()` invalidates as well (fused
+        optimizers do not bump version counters).  SDAB_ALWAYS_REPACK=1 repacks at every forward."""
 
         self._packed_key = None
 
@@ -404,7 +421,10 @@ class UNet(nn.Module):
 
         convs, projs = self._ordered_parameters()
         params = [p for m in convs + projs for p in (m.weight, m.bias)]
-        key = (device, tuple((p.data_ptr(), p._version) for p in params))
+        # (data_ptr, version) of every parameter -- and the count of optimizer steps taken in this process: fused
+        # optimizers (torch.optim.AdamW(fused=True), torch._fused_adamw_) update parameters WITHOUT bumping their
+        # version counters, so every Optimizer.step() anywhere makes the packed copies stale
+        key = (device, _optimizer_steps[0], tuple((p.data_ptr(), p._version) for p in params))
 
         if key != self._packed_key or os.environ.get('SDAB_ALWAYS_REPACK'):
             for p in params:
@@ -526,7 +546,12 @@ class UNet(nn.Module):
             # data-parallel step all-reduces 99 % of the parameters with ONE in-place collective and no bucket
             # copies (sda_b200.parallel.allreduce_gradients)
             sizes = [m.weight.numel() for m in convs] + [m.bias.numel() for m in convs]
-            flat = torch.empty(sum(sizes), dtype=torch.float32, device=g.device)
+            # (sda_b200.parallel.PeerAdamW points _grad_target at its peer-visible gradient buffer)
+            flat = getattr(self, '_grad_target', None)
+
+            if flat is None or flat.numel() != sum(sizes) or flat.device != g.device:
+                flat = torch.empty(sum(sizes), dtype=torch.float32, device=g.device)
+
             views = list(flat.split(sizes))
             dws = [v.view_as(m.weight) for v, m in zip(views[:len(convs)], convs)]
             dbs = views[len(convs):]

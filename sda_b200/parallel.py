@@ -186,4 +186,137 @@ def allreduce_gradients(module: torch.nn.Module, group=None) -> None:
             g.copy_(v.view_as(g))
 
 
-__all__ = ['shard_windows', 'ShardedMCScoreNet', 'window_range', 'shard_geometry', 'allreduce_gradients']
+class PeerAdamW(torch.optim.Optimizer):
+    r"""`torch.optim.AdamW` for data-parallel training of a module with native `UNet`s (BASELINE config 5; the
+    reference trains on one GPU with `torch.optim.AdamW`, sda/utils.py:125-143) as ONE kernel per rank and step over
+    NVLink peer memory (csrc/peer.cu: sdab_peer_adamw).
+
+    All parameters live in one flat buffer per rank, all gradients in another (the convolution gradients are
+    written there by sdab_unet_backward, the few others accumulate there through autograd); both are mapped by
+    every rank of `group`.  `step()` lets rank r read the gradients of its 1 / world slice from all ranks (peer
+    loads, added in rank order: deterministic), apply AdamW to that slice -- it holds the moments of its slice
+    only -- and store the new parameters into every rank's parameter buffer.  No all-reduce, no bucket copies, no
+    separate broadcast; the parameters stay bit-identical across the ranks.  With one rank it is a plain fused AdamW.
+
+        opt = PeerAdamW(sde, lr=2e-4, weight_decay=1e-3)      # collective; broadcasts rank 0's parameters
+        loss.backward(); opt.step(); opt.zero_grad()
+
+    `lr` is read from `param_groups[0]` at every step, so `torch.optim.lr_scheduler` works as usual."""
+
+    def __init__(self, module: torch.nn.Module, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 1e-2, group=None):
+        from . import _lib
+        from .nn import UNet
+        from .score import PeerBuffer
+
+        sharded = dist.is_available() and dist.is_initialized()
+        self.group = group if sharded else False
+        self.world = dist.get_world_size(group) if sharded else 1
+        self.rank = dist.get_rank(group) if sharded else 0
+
+        # order: per native UNet its convolution weights, then its convolution biases (the order of the library's
+        # flat gradient), then every other trainable parameter of the module
+        ordered, seen, self._nets = [], set(), []
+
+        for m in module.modules():
+            if isinstance(m, UNet) and m._native:
+                convs, _ = m._ordered_parameters()
+                ps = [c.weight for c in convs] + [c.bias for c in convs]
+
+                if all(p.requires_grad and id(p) not in seen for p in ps):
+                    self._nets.append((m, len(ordered), sum(p.numel() for p in ps), ps))
+                    ordered += ps
+                    seen.update(id(p) for p in ps)
+
+        self._convs = set(seen)
+        ordered += [p for p in module.parameters() if p.requires_grad and id(p) not in seen]
+
+        if not ordered or any(p.dtype != torch.float32 or not p.is_cuda for p in ordered):
+            raise ValueError('PeerAdamW expects trainable fp32 CUDA parameters')
+
+        device = ordered[0].device
+        n = sum(p.numel() for p in ordered)
+        quantum = 4 * self.world
+        self.numel = -(-n // quantum) * quantum
+        self.params_buf = PeerBuffer(self.numel, self.group, device)
+        self.grads_buf = PeerBuffer(self.numel, self.group, device)
+
+        for b in (self.params_buf, self.grads_buf):
+            if b.error:
+                raise RuntimeError('PeerAdamW: peer-memory buffers unavailable: ' + b.error)
+
+        flat_p, flat_g = self.params_buf.view, self.grads_buf.view
+        flat_p.zero_(), flat_g.zero_()
+        offset, self._views = 0, []
+
+        with torch.no_grad():
+            for p in ordered:
+                k = p.numel()
+                flat_p[offset:offset + k].copy_(p.reshape(-1))
+                p.data = flat_p[offset:offset + k].view_as(p)
+                self._views.append((p, flat_g[offset:offset + k].view_as(p)))
+                offset += k
+
+            if self.world > 1:
+                dist.broadcast(flat_p, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+
+        for net, start, size, _ in self._nets:
+            net._grad_target = flat_g[start:start + size]
+            net.invalidate_packed()
+
+        per = self.numel // self.world
+        self.begin, self.end = self.rank * per, (self.rank + 1) * per
+        self.m = torch.zeros(per, dtype=torch.float32, device=device)
+        self.v = torch.zeros(per, dtype=torch.float32, device=device)
+        self.steps, self._tail = 0, sum(size for _, _, size, _ in self._nets)
+        self._lib = _lib
+        super().__init__(ordered, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self.zero_grad()
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        r"""`.grad = None` for every parameter: the native backward hands autograd views of the flat gradient
+        buffer for the convolutions, which autograd keeps as they are; the few other gradients are gathered into
+        the flat buffer by `step()` with one multi-tensor copy."""
+
+        for p, _ in self._views:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise ValueError('PeerAdamW does not take a closure')
+
+        flat_g = self.grads_buf.view
+        lo, hi = flat_g.data_ptr(), flat_g.data_ptr() + 4 * flat_g.numel()
+        dst, src = [], []
+
+        for p, gview in self._views:
+            if p.grad is None:
+                gview.zero_()  # took no part in this backward
+            elif not (lo <= p.grad.data_ptr() < hi):
+                dst.append(gview), src.append(p.grad)  # not written in place: projection Linears, time embedding
+
+        if dst:
+            torch._foreach_copy_(dst, src)
+
+        g = self.param_groups[0]
+        self.steps += 1
+        lib = self._lib.load()
+
+        with torch.cuda.device(flat_g.device):
+            # every rank's gradients are complete before anyone reads them
+            self._lib.check(lib.sdab_peer_signal_wait(self.grads_buf.ptrs, self.rank, self.world, self.steps, self._lib.stream_ptr()))
+            self._lib.check(
+                lib.sdab_peer_adamw(
+                    self.grads_buf.ptrs, self.params_buf.ptrs, self.m.data_ptr(), self.v.data_ptr(), self.begin, self.end,
+                    self.rank, self.world, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+                    float(g['weight_decay']), self.steps, self.steps, self._lib.stream_ptr(),
+                )
+            )
+
+        # the parameters changed behind autograd's back (no version bump): the packed tensor-core weights are stale
+        for net, *_ in self._nets:
+            net.invalidate_packed()
+
+
+__all__ = ['shard_windows', 'ShardedMCScoreNet', 'window_range', 'shard_geometry', 'allreduce_gradients', 'PeerAdamW']

@@ -226,76 +226,66 @@ class _RawCuda:
         self.__cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
 
 
-class PeerExchange:
-    r"""The exchange step of the window-sharded score over NVLink peer memory (csrc/peer.cu): two alternating
-    buffers of `shape` fp32 per rank, allocated by the library, exported by CUDA IPC and mapped by every other
-    rank of `group` (all on one box).  `acquire()` hands out the rank's buffer of this turn, `gather()` is ONE kernel
-    that pushes the rank's shard to all peers, signals, and retires when every peer's shard has arrived.
-    Construction is collective; it raises on every rank if any rank cannot map its peers."""
+class PeerBuffer:
+    r"""One buffer of `numel` fp32 per rank in device memory owned by the library, exported by CUDA IPC and mapped
+    by every other rank of `group` (csrc/peer.cu; all ranks on one box).  `view` is the own payload as a tensor,
+    `ptrs` the ctypes array of every rank's base pointer as mapped here.  Construction is collective; `error` is
+    set instead of raising so that the caller can agree on a fallback with the other ranks."""
 
-    def __init__(self, shape, group, device):
+    def __init__(self, numel: int, group, device):
         import ctypes
 
         import torch.distributed as dist
 
         lib = _lib.load()
-        self.group, self.world, self.rank = group, dist.get_world_size(group), dist.get_rank(group)
+        sharded = dist.is_available() and dist.is_initialized() and group is not False
+        self.world = dist.get_world_size(group) if sharded else 1
+        self.rank = dist.get_rank(group) if sharded else 0
         self.header = int(lib.sdab_peer_header_bytes())
-        nbytes = 4 * int(torch.Size(shape).numel())
-        self.slots, self.uses, self.turn = [], [0, 0], 0
-        self._own, self._opened = [], []
-        error = None
+        self._own, self._opened, self.error, self.view = None, [], None, None
+        nbytes = 4 * int(numel)
+        ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        self.ptrs = (ctypes.c_void_p * self.world)()
 
         with torch.cuda.device(device):
-            for _ in range(2):
-                ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            try:
+                _lib.check(lib.sdab_peer_alloc(nbytes, ctypes.byref(ptr), handle))
+                self._own = ptr.value
+            except RuntimeError as e:
+                self.error = str(e)
 
-                try:
-                    _lib.check(lib.sdab_peer_alloc(nbytes, ctypes.byref(ptr), handle))
-                    self._own.append(ptr.value)
-                except RuntimeError as e:  # reported collectively below
-                    error = str(e)
+            handles = [handle.raw if self.error is None else None]
 
+            if self.world > 1:
                 handles = [None] * self.world
-                dist.all_gather_object(handles, None if error else handle.raw, group=group)
-                ptrs = (ctypes.c_void_p * self.world)()
+                dist.all_gather_object(handles, None if self.error else handle.raw, group=group)
 
-                for p, h in enumerate(handles):
-                    if p == self.rank:
-                        ptrs[p] = ptr.value
-                    elif h is not None and error is None:
-                        q = ctypes.c_void_p()
+            for p, h in enumerate(handles):
+                if p == self.rank:
+                    self.ptrs[p] = ptr.value
+                elif h is not None and self.error is None:
+                    q = ctypes.c_void_p()
 
-                        try:
-                            _lib.check(lib.sdab_peer_open(h, ctypes.byref(q)))
-                            self._opened.append(q.value)
-                            ptrs[p] = q.value
-                        except RuntimeError as e:
-                            error = str(e)
-                    else:
-                        error = error or f'rank {p} could not allocate its peer buffer'
+                    try:
+                        _lib.check(lib.sdab_peer_open(h, ctypes.byref(q)))
+                        self._opened.append(q.value)
+                        self.ptrs[p] = q.value
+                    except RuntimeError as e:
+                        self.error = str(e)
+                else:
+                    self.error = self.error or f'rank {p} could not allocate its peer buffer'
 
-                view = None if error else torch.as_tensor(_RawCuda(ptr.value + self.header, nbytes), device=device).view(torch.float32).view(shape)
-                self.slots.append((view, ptrs))
+            if self.world > 1:
+                errors = [None] * self.world
+                dist.all_gather_object(errors, self.error, group=group)
 
-        errors = [None] * self.world
-        dist.all_gather_object(errors, error, group=group)
+                if any(errors):
+                    self.error = '; '.join(f'rank {p}: {e}' for p, e in enumerate(errors) if e)
 
-        if any(errors):
-            self.close()
-            raise RuntimeError('peer-memory exchange unavailable: ' + '; '.join(f'rank {p}: {e}' for p, e in enumerate(errors) if e))
-
-    def acquire(self) -> Tensor:
-        self.turn ^= 1
-        self.uses[self.turn] += 1
-
-        return self.slots[self.turn][0]
-
-    def gather(self, shard_offset_bytes: int, shard_bytes: int) -> None:
-        r"""Completes the buffer handed out by the last `acquire()` (enqueued on the current stream)."""
-
-        _, ptrs = self.slots[self.turn]
-        _lib.check(_lib.load().sdab_peer_allgather(ptrs, self.rank, self.world, shard_offset_bytes, shard_bytes, self.uses[self.turn], _lib.stream_ptr()))
+            if self.error is None:
+                self.view = torch.as_tensor(_RawCuda(ptr.value + self.header, nbytes), device=device).view(torch.float32)
+            else:
+                self.close()
 
     def close(self) -> None:
         lib = _lib.load()
@@ -303,10 +293,48 @@ class PeerExchange:
         for q in self._opened:
             lib.sdab_peer_close(q)
 
-        for q in self._own:
-            lib.sdab_peer_free(q)
+        if self._own:
+            lib.sdab_peer_free(self._own)
 
-        self._opened, self._own, self.slots = [], [], []
+        self._opened, self._own, self.view = [], None, None
+
+
+class PeerExchange:
+    r"""The exchange step of the window-sharded score over NVLink peer memory (csrc/peer.cu): two alternating
+    `PeerBuffer`s of `shape` fp32 per rank.  `acquire()` hands out the rank's buffer of this turn, `gather()` is ONE
+    kernel that pushes the rank's shard to all peers, signals, and retires when every peer's shard has arrived.
+    Construction is collective; it raises on every rank if any rank cannot map its peers."""
+
+    def __init__(self, shape, group, device):
+        numel = int(torch.Size(shape).numel())
+        self.buffers = [PeerBuffer(numel, group, device) for _ in range(2)]
+        errors = [b.error for b in self.buffers if b.error]
+
+        if errors:
+            self.close()
+            raise RuntimeError('peer-memory exchange unavailable: ' + errors[0])
+
+        self.world, self.rank = self.buffers[0].world, self.buffers[0].rank
+        self.views = [b.view.view(shape) for b in self.buffers]
+        self.uses, self.turn = [0, 0], 0
+
+    def acquire(self) -> Tensor:
+        self.turn ^= 1
+        self.uses[self.turn] += 1
+
+        return self.views[self.turn]
+
+    def gather(self, shard_offset_bytes: int, shard_bytes: int) -> None:
+        r"""Completes the buffer handed out by the last `acquire()` (enqueued on the current stream)."""
+
+        ptrs = self.buffers[self.turn].ptrs
+        _lib.check(_lib.load().sdab_peer_allgather(ptrs, self.rank, self.world, shard_offset_bytes, shard_bytes, self.uses[self.turn], _lib.stream_ptr()))
+
+    def close(self) -> None:
+        for b in self.buffers:
+            b.close()
+
+        self.views = []
 
 
 def _exchange(net: UNet, key, shape, group, device):

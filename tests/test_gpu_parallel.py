@@ -68,6 +68,35 @@ def _worker(rank, world, port, results):
         both = [torch.empty_like(sample) for _ in range(world)]
         dist.all_gather(both, sample)
         ok = ok and bool(torch.isfinite(sample).all()) and all(bool(torch.equal(both[0], o)) for o in both)
+        # data-parallel training step: PeerAdamW (reduce + AdamW + broadcast over peer memory) against
+        # allreduce_gradients + torch.optim.AdamW on a copy, different data per rank
+        import copy
+
+        from sda_b200.parallel import PeerAdamW, allreduce_gradients
+
+        score, k = build_score('net_small', 16, 'cuda')
+        sde_a = sc.VPSDE(score.kernel, shape=(6, 16, 16)).cuda().train()
+        sde_b = copy.deepcopy(sde_a)
+        opt_a = torch.optim.AdamW(sde_a.parameters(), lr=1e-3, weight_decay=1e-2)
+        opt_b = PeerAdamW(sde_b, lr=1e-3, weight_decay=1e-2)
+        xb = randn((8, 6, 16, 16), seed=10 + rank).cuda()
+
+        for it in range(3):
+            for sde_, opt_, avg in ((sde_a, opt_a, True), (sde_b, opt_b, False)):
+                torch.manual_seed(7 * it + rank)
+                l = sde_.loss(xb)
+                opt_.zero_grad()
+                l.backward()
+                if avg:
+                    allreduce_gradients(sde_)
+                opt_.step()
+
+        flat = opt_b.params_buf.view.clone()
+        both = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(both, flat)
+        ok = ok and all(bool(torch.equal(both[0], o)) for o in both)  # replicas stay bit-identical
+        for pa, pb in zip(sde_a.parameters(), sde_b.parameters()):
+            ok = ok and float((pa - pb).norm() / pa.norm().clamp_min(1e-30)) < 2e-5
         results[rank] = ok
     finally:
         dist.destroy_process_group()

@@ -497,3 +497,70 @@ def test_packed_weights_follow_parameter_updates():
         state['kernel.network.heads.0.weight'] = state['kernel.network.heads.0.weight'] * 2
         score.load_state_dict(state)          # load_state_dict invalidates by itself
         assert not torch.equal(score(x, t), restored)
+
+
+def test_packed_weights_follow_fused_optimizers():
+    r"""torch.optim.AdamW(fused=True) updates parameters without bumping their version counters; the packed
+    weights must follow anyway (the cache key counts optimizer steps): fused and default AdamW train alike."""
+
+    import copy
+
+    import sda_b200.score as sc
+
+    score, _ = build_score('net_small', 16, 'cuda')
+    sde_a = sc.VPSDE(score.kernel, shape=(6, 16, 16)).cuda().train()
+    sde_b = copy.deepcopy(sde_a)
+    opt_a = torch.optim.AdamW(sde_a.parameters(), lr=1e-3)
+    opt_b = torch.optim.AdamW(sde_b.parameters(), lr=1e-3, fused=True)
+    x = randn((8, 6, 16, 16), seed=4).cuda()
+    losses = []
+
+    for it in range(4):
+        pair = []
+
+        for sde_, opt_ in ((sde_a, opt_a), (sde_b, opt_b)):
+            torch.manual_seed(it)
+            l = sde_.loss(x)
+            opt_.zero_grad()
+            l.backward()
+            opt_.step()
+            pair.append(float(l.detach()))
+
+        losses.append(pair)
+
+    # with stale packed weights the fused run would see the initial network at every step
+    assert all(abs(a - b) <= 1e-3 * abs(a) for a, b in losses), losses
+    assert losses[-1][1] != losses[0][1]
+
+
+def test_peer_adamw_matches_torch_adamw():
+    r"""sda_b200.parallel.PeerAdamW (one GPU: the fused AdamW kernel over the flat parameter buffer) follows
+    torch.optim.AdamW, the optimizer of the reference's training loop (sda/utils.py:125-143), step by step."""
+
+    import copy
+
+    import sda_b200.score as sc
+    from sda_b200.parallel import PeerAdamW
+
+    score, _ = build_score('net_small', 16, 'cuda')
+    sde_a = sc.VPSDE(score.kernel, shape=(6, 16, 16)).cuda().train()
+    sde_b = copy.deepcopy(sde_a)
+    opt_a = torch.optim.AdamW(sde_a.parameters(), lr=1e-3, weight_decay=1e-2)
+    opt_b = PeerAdamW(sde_b, lr=1e-3, weight_decay=1e-2)
+    x = randn((8, 6, 16, 16), seed=3).cuda()
+
+    for it in range(3):
+        torch.manual_seed(it)
+        la = sde_a.loss(x)
+        opt_a.zero_grad()
+        la.backward()
+        opt_a.step()
+        torch.manual_seed(it)
+        lb = sde_b.loss(x)
+        opt_b.zero_grad()
+        lb.backward()
+        opt_b.step()
+        assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(la)), (it, float(la), float(lb))
+
+    for (name, pa), (_, pb) in zip(sde_a.named_parameters(), sde_b.named_parameters()):
+        assert rel_l2(pb, pa) < 2e-5, name

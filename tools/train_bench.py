@@ -49,7 +49,23 @@ def main():
         opt.step()
         return l
 
-    if world > 1 and os.environ.get('SDAB_TRAIN_DDP'):
+    peer = os.environ.get('SDAB_TRAIN_OPT', 'peer') == 'peer' and not os.environ.get('SDAB_TRAIN_DDP')
+
+    if peer:
+        # sda_b200.parallel.PeerAdamW: gradient exchange + AdamW + parameter broadcast as one kernel per rank over
+        # NVLink peer memory (a plain fused AdamW on one GPU).  SDAB_TRAIN_OPT=torch: torch.optim.AdamW(fused=True)
+        # after allreduce_gradients
+        from sda_b200.parallel import PeerAdamW
+
+        opt = PeerAdamW(sde, lr=2e-4, weight_decay=1e-3)
+
+        def step():  # noqa: F811
+            l = sde.loss(x)
+            opt.zero_grad()
+            l.backward()
+            opt.step()
+            return l
+    elif world > 1 and os.environ.get('SDAB_TRAIN_DDP'):
         # torch DDP for comparison: its hooks fire on the parameter gradients produced by the native backward;
         # VPSDE.loss is not the module's forward, so route it through a thin wrapper module
         class Loss(torch.nn.Module):
@@ -110,7 +126,8 @@ def main():
             'workload': 'VPSDE.loss + backward + AdamW, U-Net (96, 192, 384) x (3, 3, 3), windows (10, 64, 64), '
                         f'batch 32 per GPU x {world} GPU(s)',
             'mode': os.environ.get('SDAB_MODE', 'bf16x3'), 'n_gpus': world,
-            'gradient_exchange': 'none' if world == 1 else ('torch DDP' if os.environ.get('SDAB_TRAIN_DDP') else 'flat in-place all-reduce'), 'iterations': iters,
+            'optimizer': 'PeerAdamW (csrc/peer.cu)' if peer else 'torch.optim.AdamW(fused=True)',
+            'gradient_exchange': 'peer-memory reduce + AdamW + broadcast kernel' if peer and world > 1 else 'none' if world == 1 else ('torch DDP' if os.environ.get('SDAB_TRAIN_DDP') else 'flat in-place all-reduce'), 'iterations': iters,
             'ms_per_iteration': ms / iters, 'iterations_per_s': iters / (ms * 1e-3),
             'samples_per_s': 32 * world * iters / (ms * 1e-3),
             'algorithmic_tflops': 3 * 32 * world * bench.CONV_FLOP_PER_PIXEL * 64 * 64 * iters / (ms * 1e-3) / 1e12,
