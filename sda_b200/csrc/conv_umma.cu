@@ -18,6 +18,9 @@
 //                fused bias / residual / activation / activation-derivative / bf16 split -> global).
 //                smem ring of `stages` K-blocks (full/empty mbarriers), TMEM accumulator double
 //                buffered when C_out <= 256 so the epilogue of tile i overlaps the MMAs of tile i+1.
+//                (conv_umma_patch_kernel: 384 threads -- warpgroup 0 = producer + MMA issuer, warpgroups 1, 2 = two
+//                epilogue warpgroups, registers re-divided by setmaxnreg; C_out = 384 with a fused LayerNorm builds
+//                its accumulator as three pieces in a ring of four TMEM slots.)
 #include <cudaTypedefs.h>
 
 #include <cstdlib>
