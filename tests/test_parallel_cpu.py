@@ -143,3 +143,17 @@ def test_gradient_allreduce_and_seed_broadcast():
         assert p.exitcode == 0
 
     assert dict(results) == {0: True, 1: True}
+
+
+def test_shard_windows_rejects_unknown_transport():
+    r"""`shard_windows(transport=...)`: 'peer' (default, NVLink peer-memory kernel on the fused CUDA path) or 'nccl'."""
+
+    import sda_b200.score as sc
+    from sda_b200.parallel import shard_windows
+
+    score = sc.MCScoreNet(2, order=1, hidden_features=[8], activation=torch.nn.SiLU)
+
+    with pytest.raises(ValueError):
+        shard_windows(score, transport='carrier-pigeon')
+
+    assert shard_windows(score, transport='nccl') is score and score._sdab_sharded
