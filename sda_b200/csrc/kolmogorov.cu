@@ -647,8 +647,11 @@ __global__ void __launch_bounds__(RX* RX)
   const float inv_h = 1.f / h;
   const f2 ndt_h = splat(-dt / h), ninv_h = splat(-inv_h), inv_h2 = splat(1.f / (h * h));
 
+  // programmatic dependent launch: the tables below are filled while the previous kernel of the inner step drains
+  pdl_launch_dependents();
   fill_twiddles_full(tw, N, tid, N);
   sforce[j] = sinf(4.f * ((float)j + 0.5f) * h);  // Kolmogorov forcing at u's offset y_{j+1/2}
+  pdl_wait();  // no global access above
 
   const int ea = 2 * pair, eb = 2 * pair + 1;
   const bool hasb = eb < E;  // odd ensemble: the missing partner is a zero field whose results are dropped
@@ -777,11 +780,13 @@ __global__ void __launch_bounds__(16 * RX) fused_col_solve_kernel(float2* __rest
   float2* tw = xch + 16 * LC;                    // [N]
   float* lam = reinterpret_cast<float*>(tw + N);  // [N]
   const int tid = threadIdx.x, c = tid & 15, r = tid >> 4;
+  pdl_launch_dependents();
   fill_twiddles_full(tw, N, tid, 16 * RX);
   for (int k = tid; k < N; k += 16 * RX) {
     const float s = sinpif((float)k / (float)N);
     lam[k] = -4.f * s * s / (h * h);
   }
+  pdl_wait();  // no global access above
   const int py = blockIdx.x * 16 + c;  // y frequency of this column (natural order)
   float2* base = spec + (size_t)blockIdx.y * N * N + py;
   float2* x = xch + c * LC;
@@ -832,7 +837,9 @@ __global__ void __launch_bounds__(FusedGeom<RX, RB>::kThreadsC)
   float2* tw = ql + (RB + 1) * LS;              // [N]
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * RB, pair = blockIdx.y;
+  pdl_launch_dependents();
   fill_twiddles_full(tw, N, tid, blockDim.x);
+  pdl_wait();  // no global access above
   __syncthreads();
   for (int line = tid / RX; line <= RB; line += blockDim.x / RX) {
     const int t = tid % RX;
@@ -929,6 +936,18 @@ int project(const sdab_kolmogorov* k, const float* src, float* dst, float2* spec
 }
 
 // ---------------------------------------------------------------------------- fast path (host)
+// launch with the programmatic-stream-serialization attribute (pdl_wait() in the kernel; SDAB_PDL=0: plain launch)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -957,16 +976,18 @@ int inner_step_fast(const sdab_kolmogorov* k, float* uv, float* uvs, float2* spe
   // SDAB_KOLMO_PACKED=0: the scalar march (one member after the other), kept as the cross-check of the packed one
   static const int packed = env_int("SDAB_KOLMO_PACKED", 1);
   if (packed) {
-    fused_explicit_rowfft2_kernel<RX, RB><<<dim3(N / RB, npairs), N, G::smem_a2, st>>>(uv, uvs, spec, E, k->dt_inner, k->h, k->nu);
+    SDAB_CUDA_CHECK(launch_pdl(fused_explicit_rowfft2_kernel<RX, RB>, dim3(N / RB, npairs), dim3(N), G::smem_a2, st,
+                               (const float*)uv, uvs, spec, E, k->dt_inner, k->h, k->nu));
     SDAB_LAUNCH_CHECK("fused_explicit_rowfft2_kernel");
   } else {
     fused_explicit_rowfft_kernel<RX, RB><<<dim3(N / RB, npairs), N, G::smem_a, st>>>(uv, uvs, spec, E, k->dt_inner, k->h, k->nu);
     SDAB_LAUNCH_CHECK("fused_explicit_rowfft_kernel");
   }
   constexpr size_t smem_b = (size_t)16 * (RX * (RX + 1) + 1) * sizeof(float2) + (size_t)N * sizeof(float2) + (size_t)N * sizeof(float);
-  fused_col_solve_kernel<RX><<<dim3(N / 16, npairs), 16 * RX, smem_b, st>>>(spec, k->h);
+  SDAB_CUDA_CHECK(launch_pdl(fused_col_solve_kernel<RX>, dim3(N / 16, npairs), dim3(16 * RX), smem_b, st, spec, k->h));
   SDAB_LAUNCH_CHECK("fused_col_solve_kernel");
-  fused_rowifft_grad_kernel<RX, RB><<<dim3(N / RB, npairs), G::kThreadsC, G::smem_c, st>>>(spec, uvs, uv, E, k->h);
+  SDAB_CUDA_CHECK(launch_pdl(fused_rowifft_grad_kernel<RX, RB>, dim3(N / RB, npairs), dim3(G::kThreadsC), G::smem_c, st,
+                             (const float2*)spec, (const float*)uvs, uv, E, k->h));
   SDAB_LAUNCH_CHECK("fused_rowifft_grad_kernel");
   return SDAB_OK;
 }
